@@ -1,0 +1,176 @@
+/*
+ * simuscop.h -- C ABI of the B200 read-generation hot path (libsimuscop_cuda.so).
+ *
+ * This is the drop-in boundary for the per-read loop of SimuSCoP's `simuReads`.
+ * The reference has no FFI for this path; it enters it through a C function
+ * pointer and process-wide singletons:
+ *
+ *   threadPool->pool_add_work(&Segment::yieldReads, &chrSegs[k], n++)
+ *                                     reference lib/genome/Genome.cpp:881, :949
+ *   void* Segment::yieldReads(const void* seg)      lib/segment/Segment.cpp:673-871
+ *   char* Profile::predict(char* refSeq, int isRead1)  lib/profile/Profile.cpp:1586-1701
+ *   int   Profile::yieldInsertSize()                lib/profile/Profile.cpp:1486-1493
+ *   swp->write(char*[, char*])                      lib/seqwriter/SeqWriter.cpp:41-54
+ *
+ * The entry points below are what a maintainer binds where Genome::yieldReads
+ * dispatched segments to the thread pool (INTEGRATION.md shows the stub).
+ * Conventions: plain pointers and sizes only; every function returns SSC_OK (0)
+ * or an SSC_ERR_* code and records a message readable with ssc_last_error();
+ * no exception crosses the boundary; host pointers are borrowed for the duration
+ * of the call only; one handle per GPU; a handle is not thread-safe, distinct
+ * handles may be used from distinct host threads.  There is no CPU fallback:
+ * without a CUDA device ssc_create() fails.
+ */
+#ifndef SIMUSCOP_H
+#define SIMUSCOP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSC_OK            0
+#define SSC_ERR_INVALID   1   /* bad argument / unsupported configuration */
+#define SSC_ERR_CUDA      2   /* CUDA runtime error */
+#define SSC_ERR_STATE     3   /* call order violated (e.g. generate before set_plan) */
+#define SSC_ERR_NOMEM     4
+#define SSC_ERR_SINK      5   /* the sink callback returned non-zero */
+#define SSC_ERR_OVERFLOW  6   /* a read outgrew the per-read scratch (limits) */
+
+typedef struct ssc_handle ssc_handle;
+
+/*
+ * Profile tables -- the FP64 CDFs exactly as the reference builds them
+ * (Profile::load -> normParas(true) -> initCDFs, lib/profile/Profile.cpp:934-1434;
+ * Matrix::normalize/cumsum, lib/matrix/Matrix.h:482-522).  Row-major:
+ *   subs_cdf1/2 [n_kmer_rows][bins][n_bases]      (Profile::subsCdf1/2)
+ *   quality_cdf [n_bases*n_bases][bins][n_qual]   (Profile::qualityCdf)
+ *   isize_cdf   [n_isize]  value k <-> insert size min_insert_size+k (Profile::iSizeCdf)
+ *   ins_cdf/del_cdf [n_ins]/[n_del]               (Profile::insCdf/delCdf)
+ * n_isize == 0 means "no insert-size table": every fragment uses fixed_insert_size
+ * (Profile::yieldInsertSize, Profile.cpp:1487-1489).  use_cdf2 == 0 means read 2
+ * uses subs_cdf1 (Profile::getSubBaseIndx2, Profile.cpp:1546-1549).
+ */
+typedef struct ssc_profile_tables {
+	int32_t n_bases;            /* N, must be 4 */
+	int32_t kmer;               /* K */
+	int32_t bins;               /* B */
+	int32_t n_qual;             /* Q = 94 */
+	int32_t min_qual;           /* 33 */
+	int32_t read_length;        /* RL */
+	int32_t paired;             /* layout == "PE" */
+	int32_t use_cdf2;
+	int32_t fixed_insert_size;  /* config insertSize */
+	int32_t min_insert_size;
+	int32_t n_isize;
+	int32_t n_ins;
+	int32_t n_del;
+	int32_t n_kmer_rows;        /* sum_{p=1..K} N^p */
+	double insert_rate;
+	double del_rate;
+	char bases[8];              /* e.g. "ACTG", NUL padded */
+	const double* isize_cdf;
+	const double* ins_cdf;
+	const double* del_cdf;
+	const double* subs_cdf1;
+	const double* subs_cdf2;
+	const double* quality_cdf;
+} ssc_profile_tables;
+
+/*
+ * One sampling bin of the read plan (Segment::fragStartPos/fragEndPos/hapIndxs/fragRCs,
+ * lib/segment/Segment.h:44-48), flattened so that the device needs no segment objects.
+ * Bins are given in the reference's threads=1 emission order
+ * (population -> chromosome -> segment -> bin); bins of one segment are contiguous.
+ */
+typedef struct ssc_bin {
+	int64_t hap_base;     /* index in the haplotype store of the first base of this
+	                         segment's haplotype string (segSequences[hap]) */
+	int64_t contig_end;   /* one past the last base of the (population, chromosome,
+	                         haplotype index) contig: the concatenation of the same-index
+	                         haplotype strings of the chromosome's segments, which is what
+	                         Segment::getFragSequence + Genome::produceFragment walk
+	                         (Segment.cpp:1077-1103, Genome.cpp:599-632) */
+	int32_t spos, epos;   /* start position is drawn in [spos, epos] */
+	uint32_t segsize;     /* seqSize/CN, the modulus of the position in read names */
+	int32_t read_count;   /* fragRCs[i] */
+	int32_t segment;      /* index into the segment array */
+	int32_t reserved;
+} ssc_bin;
+
+typedef struct ssc_segment {
+	int64_t first_bin;
+	int64_t n_bins;
+	int32_t name_offset;  /* "@<popu>#<chr>#" inside the name blob (Segment.cpp:780,809,824) */
+	int32_t name_len;
+} ssc_segment;
+
+typedef struct ssc_stats {
+	double   device_ms;        /* sum of CUDA-event durations of the generation kernels */
+	uint64_t launches;         /* kernels launched by this handle since creation */
+	uint64_t gen_launches;     /* launches of the fused generation kernel */
+	uint64_t pairs_emitted;
+	uint64_t reads_emitted;
+	uint64_t bases_emitted;    /* sum of emitted read lengths */
+	uint64_t fastq_bytes;      /* bytes of FASTQ written to HBM */
+	uint64_t hap_bytes;        /* algorithmic haplotype bytes read: ceil(len/4)+ceil(len/8) per fragment */
+	uint64_t d2h_bytes;
+	uint64_t h2d_bytes;
+} ssc_stats;
+
+/*
+ * Sink for finished FASTQ slabs, called in pair order.  buf1/buf2 point to pinned host
+ * memory owned by the handle and valid only during the call (SeqWriter::write(char*,char*)
+ * semantics, SeqWriter.cpp:49-54: the callee copies or writes synchronously).  In SE
+ * layout buf2 == NULL and len2 == 0.  Return 0 to continue.
+ */
+typedef int (*ssc_sink_fn)(void* user, const char* buf1, size_t len1, const char* buf2, size_t len2,
+                           int64_t first_pair, int64_t n_pairs);
+
+const char* ssc_last_error(void);
+int ssc_version(void);
+
+int ssc_create(int device, ssc_handle** out);
+int ssc_destroy(ssc_handle* h);
+
+/* "batch_pairs" (pairs per kernel launch), "fp64_search" (0/1: use the FP64 linear-search
+ * ground-truth kernel instead of the integer-threshold kernel). */
+int ssc_set_option(ssc_handle* h, const char* key, int64_t value);
+
+int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t);
+
+/* Haplotype store: 2-bit codes (in the profile's `bases` order) + 1-bit non-ACGT mask,
+ * packed on the device from ASCII (any case; every non-ACGT character behaves as N).
+ * Append the haplotype strings contig by contig; *first_base receives the store index of
+ * the first appended base. */
+int ssc_genome_reserve(ssc_handle* h, uint64_t total_bases);
+int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* first_base);
+int ssc_genome_size(ssc_handle* h, uint64_t* n_bases);
+
+/* Uploads the plan, runs the fragment census (failCount > 1000 rule, Segment.cpp:753-762)
+ * for `seed`, and computes pair / fragCount prefix sums.  *planned_pairs = number of pair
+ * IDs (PE: sum ceil(read_count/2); SE: sum read_count). */
+int ssc_set_plan(ssc_handle* h, uint64_t seed,
+                 const ssc_bin* bins, int64_t n_bins,
+                 const ssc_segment* segs, int64_t n_segs,
+                 const char* names, int64_t names_len,
+                 int64_t* planned_pairs, int64_t* emitted_pairs);
+
+/* Generates planned pair IDs [pair_lo, pair_hi) and streams the FASTQ bytes to `sink`
+ * through pinned double buffers (host copies inside). */
+int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn sink, void* user);
+
+/* Same work, output left in the handle's device slab (no device->host copy of FASTQ):
+ * the device-resident measurement leg.  Any of the out pointers may be NULL. */
+int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi,
+                        uint64_t* bytes1, uint64_t* bytes2, uint64_t* bases, double* device_ms);
+
+int ssc_get_stats(ssc_handle* h, ssc_stats* out);
+int ssc_reset_stats(ssc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
