@@ -1,0 +1,627 @@
+// api.cu -- C ABI of include/simuscop.h: device memory, plan upload, census, batched
+// generation with pinned double-buffered device->host streaming.  No CPU fallback: every
+// entry point needs a CUDA device and fails loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/simuscop.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess)                                                                    \
+			return fail(SSC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+template <class T> struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	cudaError_t alloc(size_t count) {
+		release();
+		n = count;
+		if (count == 0) return cudaSuccess;
+		return cudaMalloc((void**)&p, count * sizeof(T));
+	}
+	cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+		cudaError_t e = alloc(v.size());
+		if (e != cudaSuccess || v.empty()) return e;
+		return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct ssc_handle {
+	int device = 0;
+	int smCount = 0;
+	int smemLimit = 0;
+	cudaStream_t compute = nullptr, copy = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evGen[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
+
+	// options
+	int64_t batchPairs = 1 << 20;
+	bool fp64 = false;
+
+	// profile
+	bool haveProfile = false;
+	ssc::DeviceTablesHost th;
+	ssc::DevTables dt;
+	DevBuf<uint32_t> d_isizeT, d_insT, d_delT, d_qualT;
+	DevBuf<uint16_t> d_isizeSym, d_insSym, d_delSym;
+	DevBuf<uint8_t> d_qualSym;
+	DevBuf<uint4> d_sub;
+	DevBuf<double> d_fIsize, d_fIns, d_fDel, d_fSub1, d_fSub2, d_fQual;
+	DevBuf<int8_t> d_lut;
+
+	// genome
+	DevBuf<uint32_t> d_hap2, d_hapN;
+	uint64_t genomeCap = 0, genomeSize = 0;
+	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
+	uint8_t* d_stage[2] = {nullptr, nullptr};
+	cudaEvent_t evStage[2] = {nullptr, nullptr};
+	size_t stageBytes = 32u << 20;
+
+	// plan
+	bool havePlan = false;
+	uint64_t seed = 0;
+	std::vector<int64_t> planBaseAll, emitBaseAll;   // per original bin (+1 sentinel)
+	DevBuf<ssc::DevBin> d_bins;
+	DevBuf<int64_t> d_emitBase;
+	DevBuf<uint16_t> d_risky;
+	DevBuf<char> d_names;
+	int64_t nDevBins = 0, plannedPairs = 0, emittedPairs = 0;
+	int maxRecBytes = 0;
+
+	// batch resources
+	int64_t slabPairs = 0;
+	uint64_t slabCap = 0;
+	uint8_t* d_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][file]
+	uint8_t* h_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+	DevBuf<int32_t> d_tileStart[2];
+	DevBuf<unsigned long long> d_tileState[2];
+	DevBuf<unsigned int> d_ticket[2];
+	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
+	ssc::BatchResult* h_result[2] = {nullptr, nullptr};
+
+	ssc_stats stats;
+};
+
+namespace {
+
+int ensure_batch_resources(ssc_handle* h, bool needHost) {
+	int64_t pairs = std::min<int64_t>(h->batchPairs, std::max<int64_t>(h->emittedPairs, 1));
+	pairs = ((pairs + GEN_TILE_PAIRS - 1) / GEN_TILE_PAIRS) * GEN_TILE_PAIRS;
+	uint64_t cap = (uint64_t)pairs * (uint64_t)h->maxRecBytes + 4096;
+	if (cap >= (1ull << 31)) {
+		pairs = (int64_t)(((1ull << 31) - 8192) / (uint64_t)h->maxRecBytes);
+		pairs = (pairs / GEN_TILE_PAIRS) * GEN_TILE_PAIRS;
+		if (pairs <= 0) return fail(SSC_ERR_INVALID, "record size too large");
+		cap = (uint64_t)pairs * (uint64_t)h->maxRecBytes + 4096;
+	}
+	int nFiles = h->dt.paired ? 2 : 1;
+	if (pairs != h->slabPairs || cap != h->slabCap) {
+		for (int b = 0; b < 2; b++)
+			for (int f = 0; f < 2; f++) {
+				if (h->d_out[b][f]) cudaFree(h->d_out[b][f]);
+				if (h->h_out[b][f]) cudaFreeHost(h->h_out[b][f]);
+				h->d_out[b][f] = nullptr; h->h_out[b][f] = nullptr;
+			}
+		h->slabPairs = pairs; h->slabCap = cap;
+		int nTiles = (int)(pairs / GEN_TILE_PAIRS);
+		for (int b = 0; b < 2; b++) {
+			for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_out[b][f], cap));
+			CK(h->d_tileStart[b].alloc(nTiles));
+			CK(h->d_tileState[b].alloc(nTiles));
+			CK(h->d_ticket[b].alloc(1));
+		}
+	}
+	if (needHost)
+		for (int b = 0; b < 2; b++)
+			for (int f = 0; f < nFiles; f++)
+				if (!h->h_out[b][f]) CK(cudaMallocHost((void**)&h->h_out[b][f], h->slabCap));
+	return SSC_OK;
+}
+
+// emitted-pair index of the first emitted pair whose planned ID is >= p
+int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
+	if (p <= 0) return 0;
+	if (p >= h->plannedPairs) return h->emittedPairs;
+	const std::vector<int64_t>& pb = h->planBaseAll;
+	size_t b = std::upper_bound(pb.begin(), pb.end(), p) - pb.begin() - 1;   // pb[b] <= p < pb[b+1]
+	int64_t emitCount = h->emitBaseAll[b + 1] - h->emitBaseAll[b];
+	return h->emitBaseAll[b] + std::min<int64_t>(p - pb[b], emitCount);
+}
+
+int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
+	int nTiles = (int)((emitHi - emitLo + GEN_TILE_PAIRS - 1) / GEN_TILE_PAIRS);
+	cudaStream_t s = h->compute;
+	CK(cudaMemsetAsync(h->d_tileState[buf].p, 0, sizeof(unsigned long long) * nTiles, s));
+	CK(cudaMemsetAsync(h->d_ticket[buf].p, 0, sizeof(unsigned int), s));
+	CK(cudaMemsetAsync(h->d_result[buf], 0, sizeof(ssc::BatchResult), s));
+	CK(ssc::launch_locate(h->d_emitBase.p, h->nDevBins, emitLo, nTiles, h->d_tileStart[buf].p, s));
+	ssc::GenParams P;
+	P.t = h->dt;
+	P.hap2 = h->d_hap2.p; P.hapN = h->d_hapN.p;
+	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
+	P.riskyAttempt = h->d_risky.p; P.names = h->d_names.p;
+	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi;
+	P.tileStartBin = h->d_tileStart[buf].p; P.nTiles = nTiles;
+	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p;
+	P.out1 = h->d_out[buf][0]; P.out2 = h->d_out[buf][1];
+	P.cap1 = h->slabCap; P.cap2 = h->slabCap;
+	P.result = h->d_result[buf];
+	ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
+	if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
+	int grid = std::min(nTiles, h->smCount);
+	CK(ssc::launch_generate(P, v, grid, s));
+	CK(cudaMemcpyAsync(h->h_result[buf], h->d_result[buf], sizeof(ssc::BatchResult), cudaMemcpyDeviceToHost, s));
+	h->stats.launches += 2;
+	h->stats.gen_launches += 1;
+	return SSC_OK;
+}
+
+int check_result(ssc_handle* h, const ssc::BatchResult& r) {
+	if (r.errorFlags & 1u) return fail(SSC_ERR_OVERFLOW, "output slab overflow (internal capacity estimate too small)");
+	if (r.errorFlags & 2u) return fail(SSC_ERR_OVERFLOW, "a read outgrew the per-read scratch (insertions > 96 bases)");
+	if (r.errorFlags & 4u) return fail(SSC_ERR_OVERFLOW, "more than 32 indel events or 128 inserted bases in one read");
+	h->stats.pairs_emitted += r.pairs;
+	h->stats.reads_emitted += r.reads;
+	h->stats.bases_emitted += r.bases;
+	h->stats.fastq_bytes += r.bytes1 + r.bytes2;
+	h->stats.hap_bytes += r.hapBytes;
+	return SSC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ssc_last_error(void) { return g_err.c_str(); }
+int ssc_version(void) { return 1; }
+
+int ssc_create(int device, ssc_handle** out) {
+	if (!out) return fail(SSC_ERR_INVALID, "out is null");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(SSC_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0 || device >= count) return fail(SSC_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+	CK(cudaSetDevice(device));
+	ssc_handle* h = new ssc_handle();
+	h->device = device;
+	memset(&h->stats, 0, sizeof(h->stats));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	h->smCount = prop.multiProcessorCount;
+	h->smemLimit = (int)prop.sharedMemPerBlockOptin - 1024;
+	CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&h->evStart));
+	CK(cudaEventCreate(&h->evStop));
+	for (int i = 0; i < 2; i++) {
+		CK(cudaEventCreateWithFlags(&h->evGen[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evCopy[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evStage[i], cudaEventDisableTiming));
+		CK(cudaMalloc((void**)&h->d_result[i], sizeof(ssc::BatchResult)));
+		CK(cudaMallocHost((void**)&h->h_result[i], sizeof(ssc::BatchResult)));
+	}
+	*out = h;
+	return SSC_OK;
+}
+
+int ssc_destroy(ssc_handle* h) {
+	if (!h) return SSC_OK;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	for (int b = 0; b < 2; b++) {
+		for (int f = 0; f < 2; f++) {
+			if (h->d_out[b][f]) cudaFree(h->d_out[b][f]);
+			if (h->h_out[b][f]) cudaFreeHost(h->h_out[b][f]);
+		}
+		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
+		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
+		if (h->d_result[b]) cudaFree(h->d_result[b]);
+		if (h->h_result[b]) cudaFreeHost(h->h_result[b]);
+		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();
+		if (h->evGen[b]) cudaEventDestroy(h->evGen[b]);
+		if (h->evCopy[b]) cudaEventDestroy(h->evCopy[b]);
+		if (h->evStage[b]) cudaEventDestroy(h->evStage[b]);
+	}
+	h->d_isizeT.release(); h->d_insT.release(); h->d_delT.release(); h->d_qualT.release();
+	h->d_isizeSym.release(); h->d_insSym.release(); h->d_delSym.release(); h->d_qualSym.release();
+	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
+	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
+	h->d_hap2.release(); h->d_hapN.release();
+	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
+	if (h->evStart) cudaEventDestroy(h->evStart);
+	if (h->evStop) cudaEventDestroy(h->evStop);
+	if (h->compute) cudaStreamDestroy(h->compute);
+	if (h->copy) cudaStreamDestroy(h->copy);
+	delete h;
+	return SSC_OK;
+}
+
+int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
+	if (!h || !key) return fail(SSC_ERR_INVALID, "null argument");
+	if (!strcmp(key, "batch_pairs")) {
+		if (value < GEN_TILE_PAIRS) return fail(SSC_ERR_INVALID, "batch_pairs must be >= %d", GEN_TILE_PAIRS);
+		h->batchPairs = value;
+		return SSC_OK;
+	}
+	if (!strcmp(key, "fp64_search")) {
+		if (h->havePlan) return fail(SSC_ERR_STATE, "fp64_search must be set before ssc_set_plan");
+		h->fp64 = value != 0;
+		return SSC_OK;
+	}
+	return fail(SSC_ERR_INVALID, "unknown option %s", key);
+}
+
+int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
+	if (!h || !t) return fail(SSC_ERR_INVALID, "null argument");
+	CK(cudaSetDevice(h->device));
+	const char* err = ssc::build_tables(t, &h->th);
+	if (err[0]) return fail(SSC_ERR_INVALID, "profile rejected: %s", err);
+	if (t->read_length > 320) return fail(SSC_ERR_INVALID, "read_length %d > 320 is not supported", t->read_length);
+	cudaStream_t s = h->compute;
+	ssc::DeviceTablesHost& th = h->th;
+	CK(h->d_isizeT.upload(th.isize.T, s)); CK(h->d_isizeSym.upload(th.isize.sym, s));
+	CK(h->d_insT.upload(th.insLen.T, s)); CK(h->d_insSym.upload(th.insLen.sym, s));
+	CK(h->d_delT.upload(th.delLen.T, s)); CK(h->d_delSym.upload(th.delLen.sym, s));
+	CK(h->d_qualT.upload(th.qualT, s)); CK(h->d_qualSym.upload(th.qualSym, s));
+	std::vector<uint4> sub(th.sub.size());
+	for (size_t i = 0; i < sub.size(); i++) sub[i] = make_uint4(th.sub[i].s0, th.sub[i].s1, th.sub[i].s2, th.sub[i].base);
+	CK(h->d_sub.upload(sub, s));
+	std::vector<int8_t> lut(th.asciiCode, th.asciiCode + 256);
+	CK(h->d_lut.upload(lut, s));
+	size_t nsub = (size_t)th.nRows * th.B * 4, nq = (size_t)16 * th.B * th.Q;
+	auto up = [&](DevBuf<double>& d, const double* p, size_t n) -> cudaError_t {
+		std::vector<double> v(p ? p : nullptr, p ? p + n : nullptr);
+		return d.upload(v, s);
+	};
+	CK(up(h->d_fIsize, t->isize_cdf, t->n_isize > 0 ? t->n_isize : 0));
+	CK(up(h->d_fIns, t->ins_cdf, t->n_ins));
+	CK(up(h->d_fDel, t->del_cdf, t->n_del));
+	CK(up(h->d_fSub1, t->subs_cdf1, nsub));
+	CK(up(h->d_fSub2, t->use_cdf2 ? t->subs_cdf2 : nullptr, t->use_cdf2 ? nsub : 0));
+	CK(up(h->d_fQual, t->quality_cdf, nq));
+	CK(cudaStreamSynchronize(s));
+
+	ssc::DevTables& d = h->dt;
+	memset(&d, 0, sizeof(d));
+	d.N = th.N; d.K = th.K; d.B = th.B; d.Q = th.Q; d.minQ = th.minQ; d.RL = th.RL; d.paired = th.paired;
+	d.useCdf2 = th.useCdf2; d.fixedInsert = th.fixedInsert; d.minIS = th.minIS; d.nRows = th.nRows;
+	d.insT = th.insT; d.delT = th.delT; d.insEnable = th.insEnable; d.delEnable = th.delEnable;
+	d.nIsize = (int)th.isize.T.size(); d.nInsLen = (int)th.insLen.T.size(); d.nDelLen = (int)th.delLen.T.size();
+	d.isizeT = h->d_isizeT.p; d.isizeSym = h->d_isizeSym.p;
+	d.insLenT = h->d_insT.p; d.insLenSym = h->d_insSym.p;
+	d.delLenT = h->d_delT.p; d.delLenSym = h->d_delSym.p;
+	d.sub = h->d_sub.p; d.nSub = th.nRows * th.B;
+	d.qualT = h->d_qualT.p; d.qualSym = h->d_qualSym.p; d.qualPitch = th.qualPitch; d.nQualRows = 16 * th.B;
+	d.compLut = th.compLut;
+	d.baseChars = (uint32_t)(uint8_t)th.baseChar[0] | ((uint32_t)(uint8_t)th.baseChar[1] << 8) |
+	              ((uint32_t)(uint8_t)th.baseChar[2] << 16) | ((uint32_t)(uint8_t)th.baseChar[3] << 24);
+	d.f_isize = h->d_fIsize.p; d.f_ins = h->d_fIns.p; d.f_del = h->d_fDel.p;
+	d.f_sub1 = h->d_fSub1.p; d.f_sub2 = h->d_fSub2.p; d.f_qual = h->d_fQual.p;
+	d.f_nIsize = t->n_isize; d.f_nIns = t->n_ins; d.f_nDel = t->n_del;
+	d.insertRate = t->insert_rate;
+	volatile double one_minus = 1 - t->insert_rate;
+	d.delThresh = t->del_rate / one_minus;
+	h->haveProfile = true;
+	h->havePlan = false;
+	return SSC_OK;
+}
+
+int ssc_genome_reserve(ssc_handle* h, uint64_t total_bases) {
+	if (!h) return fail(SSC_ERR_INVALID, "null handle");
+	if (!h->haveProfile) return fail(SSC_ERR_STATE, "ssc_set_profile must precede ssc_genome_reserve (codes follow the profile's base order)");
+	CK(cudaSetDevice(h->device));
+	uint64_t groups = (total_bases + 31) / 32 + 2;
+	CK(h->d_hap2.alloc(groups * 2 + 64));
+	CK(h->d_hapN.alloc(groups + 64));
+	CK(cudaMemsetAsync(h->d_hap2.p, 0, (groups * 2 + 64) * 4, h->compute));
+	CK(cudaMemsetAsync(h->d_hapN.p, 0, (groups + 64) * 4, h->compute));
+	for (int i = 0; i < 2; i++) {
+		if (!h->h_stage[i]) CK(cudaMallocHost((void**)&h->h_stage[i], h->stageBytes));
+		if (!h->d_stage[i]) CK(cudaMalloc((void**)&h->d_stage[i], h->stageBytes));
+	}
+	h->genomeCap = total_bases;
+	h->genomeSize = 0;
+	h->havePlan = false;
+	return SSC_OK;
+}
+
+int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* first_base) {
+	if (!h || (!ascii && n)) return fail(SSC_ERR_INVALID, "null argument");
+	if (h->genomeSize + n > h->genomeCap) return fail(SSC_ERR_INVALID, "genome append exceeds the reserved %llu bases", (unsigned long long)h->genomeCap);
+	CK(cudaSetDevice(h->device));
+	if (first_base) *first_base = h->genomeSize;
+	uint64_t done = 0;
+	int k = 0;
+	while (done < n) {
+		uint64_t chunk = std::min<uint64_t>(h->stageBytes, n - done);
+		CK(cudaEventSynchronize(h->evStage[k]));           // staging buffer k free again
+		memcpy(h->h_stage[k], ascii + done, chunk);
+		CK(cudaMemcpyAsync(h->d_stage[k], h->h_stage[k], chunk, cudaMemcpyHostToDevice, h->compute));
+		CK(ssc::launch_pack(h->d_stage[k], chunk, h->genomeSize + done, h->d_hap2.p, h->d_hapN.p, h->d_lut.p, h->compute));
+		CK(cudaEventRecord(h->evStage[k], h->compute));
+		h->stats.launches += 1;
+		h->stats.h2d_bytes += chunk;
+		done += chunk;
+		k ^= 1;
+	}
+	h->genomeSize += n;
+	return SSC_OK;
+}
+
+int ssc_genome_size(ssc_handle* h, uint64_t* n_bases) {
+	if (!h || !n_bases) return fail(SSC_ERR_INVALID, "null argument");
+	*n_bases = h->genomeSize;
+	return SSC_OK;
+}
+
+int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bins, const ssc_segment* segs,
+                 int64_t n_segs, const char* names, int64_t names_len, int64_t* planned_pairs, int64_t* emitted_pairs) {
+	if (!h || (!bins && n_bins) || (!segs && n_segs)) return fail(SSC_ERR_INVALID, "null argument");
+	if (!h->haveProfile) return fail(SSC_ERR_STATE, "ssc_set_profile must precede ssc_set_plan");
+	CK(cudaSetDevice(h->device));
+	const ssc::DevTables& t = h->dt;
+	const int RL = t.RL;
+	const bool paired = t.paired != 0;
+	h->seed = seed;
+	h->havePlan = false;
+
+	// ---- validate, planned pairs, risky bins
+	std::vector<int64_t>& pb = h->planBaseAll;
+	pb.assign(n_bins + 1, 0);
+	std::vector<int32_t> planned(n_bins), emit(n_bins);
+	std::vector<ssc::CensusBin> census;
+	std::vector<int64_t> censusOf;            // census index -> bin
+	std::vector<int32_t> riskyBase(n_bins, -1);
+	int64_t riskyTotal = 0;
+	int maxName = 0;
+	for (int64_t s = 0; s < n_segs; s++) {
+		if (segs[s].first_bin < 0 || segs[s].n_bins < 0 || segs[s].first_bin + segs[s].n_bins > n_bins)
+			return fail(SSC_ERR_INVALID, "segment %lld: bin range out of bounds", (long long)s);
+		if (segs[s].name_len < 0 || segs[s].name_len > 64 || segs[s].name_offset < 0 || segs[s].name_offset + segs[s].name_len > names_len)
+			return fail(SSC_ERR_INVALID, "segment %lld: bad name (max 64 bytes)", (long long)s);
+		maxName = std::max(maxName, (int)segs[s].name_len);
+	}
+	for (int64_t i = 0; i < n_bins; i++) {
+		const ssc_bin& b = bins[i];
+		int64_t n = b.read_count > 0 ? (paired ? ((int64_t)b.read_count + 1) / 2 : (int64_t)b.read_count) : 0;
+		if (n > 0) {
+			if (b.segment < 0 || b.segment >= n_segs) return fail(SSC_ERR_INVALID, "bin %lld: bad segment", (long long)i);
+			if (b.spos < 0 || b.epos < b.spos) return fail(SSC_ERR_INVALID, "bin %lld: bad range", (long long)i);
+			if (b.segsize == 0) return fail(SSC_ERR_INVALID, "bin %lld: segsize 0 (copy number 0 segments cannot emit reads)", (long long)i);
+			if (b.hap_base < 0 || b.contig_end < b.hap_base || (uint64_t)b.contig_end > h->genomeSize)
+				return fail(SSC_ERR_INVALID, "bin %lld: haplotype range outside the store", (long long)i);
+			if (n > 0x7fffffff) return fail(SSC_ERR_INVALID, "bin %lld: too many reads", (long long)i);
+		}
+		planned[i] = (int32_t)n;
+		emit[i] = (int32_t)n;
+		pb[i + 1] = pb[i] + n;
+		if (n > 0) {
+			// an attempt fails iff min(want, contig_end - (hap_base+pos)) < RL  (Segment.cpp:753)
+			bool risky = (int64_t)b.epos > b.contig_end - b.hap_base - RL;
+			if (!paired && ((int64_t)b.epos - b.spos + 1) < RL) risky = true;
+			if (paired && t.nIsize == 0 && t.fixedInsert < RL) risky = true;
+			if (risky) {
+				ssc::CensusBin c;
+				c.hap_base = b.hap_base; c.contig_end = b.contig_end; c.plan_base = pb[i];
+				c.spos = b.spos; c.epos = b.epos; c.planned = (int32_t)n; c.risky_base = (int32_t)riskyTotal;
+				if (riskyTotal + n > 0x7fffffff) return fail(SSC_ERR_INVALID, "too many pairs in bins that can fail");
+				riskyBase[i] = (int32_t)riskyTotal;
+				riskyTotal += n;
+				census.push_back(c);
+				censusOf.push_back(i);
+			}
+		}
+	}
+	h->plannedPairs = pb[n_bins];
+
+	// ---- census on the device
+	cudaStream_t s = h->compute;
+	CK(h->d_risky.alloc((size_t)std::max<int64_t>(riskyTotal, 1)));
+	if (!census.empty()) {
+		DevBuf<ssc::CensusBin> d_census;
+		DevBuf<int32_t> d_emitted;
+		CK(d_census.upload(census, s));
+		CK(d_emitted.alloc(census.size()));
+		CK(ssc::launch_census(t, h->fp64, d_census.p, (int)census.size(), seed, h->d_risky.p, d_emitted.p, s));
+		std::vector<int32_t> em(census.size());
+		CK(cudaMemcpyAsync(em.data(), d_emitted.p, em.size() * 4, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		h->stats.launches += 1;
+		for (size_t k = 0; k < census.size(); k++) emit[censusOf[k]] = em[k];
+		d_census.release(); d_emitted.release();
+	}
+
+	// ---- prefix sums, compaction
+	std::vector<int64_t>& eb = h->emitBaseAll;
+	eb.assign(n_bins + 1, 0);
+	for (int64_t i = 0; i < n_bins; i++) eb[i + 1] = eb[i] + emit[i];
+	h->emittedPairs = eb[n_bins];
+	std::vector<ssc::DevBin> dev;
+	std::vector<int64_t> devEmitBase;
+	dev.reserve(n_bins);
+	for (int64_t sIdx = 0; sIdx < n_segs; sIdx++) {
+		int64_t fragBase = 0;
+		for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
+			if (emit[i] > 0) {
+				if (bins[i].segment != sIdx) return fail(SSC_ERR_INVALID, "bin %lld does not belong to segment %lld", (long long)i, (long long)sIdx);
+				if (fragBase + emit[i] > 0x7fffffff) return fail(SSC_ERR_INVALID, "segment %lld: fragment counter overflow", (long long)sIdx);
+				ssc::DevBin d;
+				d.hap_base = bins[i].hap_base; d.contig_end = bins[i].contig_end;
+				d.plan_base = pb[i]; d.emit_base = eb[i];
+				d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
+				d.frag_base = (int32_t)fragBase;
+				d.name_off = segs[sIdx].name_offset; d.name_len = segs[sIdx].name_len;
+				d.risky_base = riskyBase[i]; d.pad = 0;
+				dev.push_back(d);
+				devEmitBase.push_back(eb[i]);
+			}
+			fragBase += emit[i];
+		}
+	}
+	// bins must be listed segment by segment in order, otherwise emit order != bin order
+	for (size_t k = 1; k < devEmitBase.size(); k++)
+		if (devEmitBase[k] <= devEmitBase[k - 1]) return fail(SSC_ERR_INVALID, "segments must list their bins in increasing, non-overlapping order");
+	devEmitBase.push_back(h->emittedPairs);
+	h->nDevBins = (int64_t)dev.size();
+	CK(h->d_bins.upload(dev, s));
+	CK(h->d_emitBase.upload(devEmitBase, s));
+	std::vector<char> nm(names, names + names_len);
+	nm.push_back(0);
+	CK(h->d_names.upload(nm, s));
+	CK(cudaStreamSynchronize(s));
+	h->stats.h2d_bytes += dev.size() * sizeof(ssc::DevBin) + devEmitBase.size() * 8;
+	// worst-case record bytes per pair per file: header + 2*(RL + 96) + 4
+	h->maxRecBytes = maxName + 10 + 1 + 10 + 3 + 2 * (RL + 16) + 4;
+	h->havePlan = true;
+	if (planned_pairs) *planned_pairs = h->plannedPairs;
+	if (emitted_pairs) *emitted_pairs = h->emittedPairs;
+	return SSC_OK;
+}
+
+int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn sink, void* user) {
+	if (!h || !sink) return fail(SSC_ERR_INVALID, "null argument");
+	if (!h->havePlan) return fail(SSC_ERR_STATE, "ssc_set_plan must precede ssc_generate");
+	if (pair_lo < 0 || pair_hi < pair_lo) return fail(SSC_ERR_INVALID, "bad pair range");
+	CK(cudaSetDevice(h->device));
+	int rc = ensure_batch_resources(h, true);
+	if (rc) return rc;
+	const int64_t eLo = emit_index_of_plan(h, pair_lo), eHi = emit_index_of_plan(h, pair_hi);
+	if (eHi <= eLo) return SSC_OK;
+	const int nFiles = h->dt.paired ? 2 : 1;
+	struct Batch { int64_t lo, hi; };
+	std::vector<Batch> batches;
+	for (int64_t e = eLo; e < eHi; e += h->slabPairs) batches.push_back({e, std::min(eHi, e + h->slabPairs)});
+	const int nb = (int)batches.size();
+	// pipeline: kernel(k+1) overlaps the device->host copy of batch k, which overlaps the sink of batch k-1
+	rc = launch_batch(h, 0, batches[0].lo, batches[0].hi);
+	if (rc) return rc;
+	CK(cudaEventRecord(h->evGen[0], h->compute));
+	ssc::BatchResult res[2];
+	for (int k = 0; k < nb; k++) {
+		const int buf = k & 1;
+		CK(cudaEventSynchronize(h->evGen[buf]));
+		res[buf] = *h->h_result[buf];
+		rc = check_result(h, res[buf]);
+		if (rc) { cudaDeviceSynchronize(); return rc; }
+		CK(cudaMemcpyAsync(h->h_out[buf][0], h->d_out[buf][0], res[buf].bytes1, cudaMemcpyDeviceToHost, h->copy));
+		if (nFiles == 2) CK(cudaMemcpyAsync(h->h_out[buf][1], h->d_out[buf][1], res[buf].bytes2, cudaMemcpyDeviceToHost, h->copy));
+		CK(cudaEventRecord(h->evCopy[buf], h->copy));
+		h->stats.d2h_bytes += res[buf].bytes1 + res[buf].bytes2;
+		if (k >= 1) {
+			// sink batch k-1 (its copy was issued in the previous iteration)
+			const int pb = (k - 1) & 1;
+			CK(cudaEventSynchronize(h->evCopy[pb]));
+			if (k + 1 < nb) {
+				// device slab pb is free again: launch batch k+1 into it before the host-side sink work
+				rc = launch_batch(h, pb, batches[k + 1].lo, batches[k + 1].hi);
+				if (rc) return rc;
+				CK(cudaEventRecord(h->evGen[pb], h->compute));
+			}
+			int src = sink(user, (const char*)h->h_out[pb][0], res[pb].bytes1, nFiles == 2 ? (const char*)h->h_out[pb][1] : nullptr,
+			               nFiles == 2 ? res[pb].bytes2 : 0, batches[k - 1].lo, batches[k - 1].hi - batches[k - 1].lo);
+			if (src) { cudaDeviceSynchronize(); return fail(SSC_ERR_SINK, "sink returned %d", src); }
+		} else if (nb > 1) {
+			rc = launch_batch(h, 1, batches[1].lo, batches[1].hi);
+			if (rc) return rc;
+			CK(cudaEventRecord(h->evGen[1], h->compute));
+		}
+	}
+	{
+		const int pb = (nb - 1) & 1;
+		CK(cudaEventSynchronize(h->evCopy[pb]));
+		int src = sink(user, (const char*)h->h_out[pb][0], res[pb].bytes1, nFiles == 2 ? (const char*)h->h_out[pb][1] : nullptr,
+		               nFiles == 2 ? res[pb].bytes2 : 0, batches[nb - 1].lo, batches[nb - 1].hi - batches[nb - 1].lo);
+		if (src) return fail(SSC_ERR_SINK, "sink returned %d", src);
+	}
+	return SSC_OK;
+}
+
+int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_t* bytes1, uint64_t* bytes2,
+                        uint64_t* bases, double* device_ms) {
+	if (!h) return fail(SSC_ERR_INVALID, "null handle");
+	if (!h->havePlan) return fail(SSC_ERR_STATE, "ssc_set_plan must precede ssc_generate_device");
+	if (pair_lo < 0 || pair_hi < pair_lo) return fail(SSC_ERR_INVALID, "bad pair range");
+	CK(cudaSetDevice(h->device));
+	int rc = ensure_batch_resources(h, false);
+	if (rc) return rc;
+	const int64_t eLo = emit_index_of_plan(h, pair_lo), eHi = emit_index_of_plan(h, pair_hi);
+	uint64_t b1 = 0, b2 = 0, nb = 0;
+	float ms = 0;
+	if (eHi > eLo) {
+		CK(cudaEventRecord(h->evStart, h->compute));
+		int k = 0;
+		for (int64_t e = eLo; e < eHi; e += h->slabPairs, k++) {
+			const int buf = k & 1;
+			if (k >= 2) {
+				CK(cudaEventSynchronize(h->evGen[buf]));
+				ssc::BatchResult r = *h->h_result[buf];
+				rc = check_result(h, r);
+				if (rc) { cudaDeviceSynchronize(); return rc; }
+				b1 += r.bytes1; b2 += r.bytes2; nb += r.bases;
+			}
+			rc = launch_batch(h, buf, e, std::min(eHi, e + h->slabPairs));
+			if (rc) return rc;
+			CK(cudaEventRecord(h->evGen[buf], h->compute));
+		}
+		CK(cudaEventRecord(h->evStop, h->compute));
+		CK(cudaEventSynchronize(h->evStop));
+		for (int j = std::max(0, k - 2); j < k; j++) {
+			ssc::BatchResult r = *h->h_result[j & 1];
+			rc = check_result(h, r);
+			if (rc) return rc;
+			b1 += r.bytes1; b2 += r.bytes2; nb += r.bases;
+		}
+		CK(cudaEventElapsedTime(&ms, h->evStart, h->evStop));
+		h->stats.device_ms += ms;
+	}
+	if (bytes1) *bytes1 = b1;
+	if (bytes2) *bytes2 = b2;
+	if (bases) *bases = nb;
+	if (device_ms) *device_ms = ms;
+	return SSC_OK;
+}
+
+int ssc_get_stats(ssc_handle* h, ssc_stats* out) {
+	if (!h || !out) return fail(SSC_ERR_INVALID, "null argument");
+	*out = h->stats;
+	return SSC_OK;
+}
+
+int ssc_reset_stats(ssc_handle* h) {
+	if (!h) return fail(SSC_ERR_INVALID, "null handle");
+	memset(&h->stats, 0, sizeof(h->stats));
+	return SSC_OK;
+}
+
+}  // extern "C"

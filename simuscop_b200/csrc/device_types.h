@@ -1,0 +1,76 @@
+// device_types.h -- structures shared between the host runtime (api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+
+namespace ssc {
+
+// Compacted device bin (only bins that emit at least one pair), 64 bytes.
+struct DevBin {
+	int64_t hap_base;     // store index of segSequences[hap][0]
+	int64_t contig_end;   // clip limit of the (population, chromosome, haplotype) contig
+	int64_t plan_base;    // first planned pair ID of the bin (Philox key)
+	int64_t emit_base;    // first emitted-pair index of the bin (output order)
+	int32_t spos, epos;
+	uint32_t segsize;
+	int32_t frag_base;    // emitted pairs in earlier bins of the same segment (fragCount - 1 of ordinal 0)
+	int32_t name_off, name_len;
+	int32_t risky_base;   // index into riskyAttempt of ordinal 0, or -1 when attempt 0 always succeeds
+	int32_t pad;
+};
+static_assert(sizeof(DevBin) == 64, "DevBin must be 64 bytes");
+
+// Bin as seen by the census kernel (every bin flagged risky by the host).
+struct CensusBin {
+	int64_t hap_base, contig_end, plan_base;
+	int32_t spos, epos;
+	int32_t planned;      // planned pairs
+	int32_t risky_base;
+};
+
+struct DevTables {
+	int N, K, B, Q, minQ, RL, paired, useCdf2, fixedInsert, minIS, nRows;
+	uint32_t insT, delT;
+	int insEnable, delEnable;
+	int nIsize, nInsLen, nDelLen;            // compressed lengths
+	const uint32_t* isizeT; const uint16_t* isizeSym;
+	const uint32_t* insLenT; const uint16_t* insLenSym;
+	const uint32_t* delLenT; const uint16_t* delLenSym;
+	const uint4* sub; int nSub;              // rows*B per read table; table of read 2 follows when useCdf2
+	const uint32_t* qualT; const uint8_t* qualSym; int qualPitch; int nQualRows;
+	uint32_t compLut;
+	uint32_t baseChars;                      // 4 ASCII characters, code i in byte i
+	// FP64 ground-truth tables (the reference's own arrays)
+	const double* f_isize; const double* f_ins; const double* f_del;
+	const double* f_sub1; const double* f_sub2; const double* f_qual;
+	int f_nIsize, f_nIns, f_nDel;
+	double insertRate, delThresh;
+};
+
+struct BatchResult {
+	unsigned long long bytes1, bytes2;
+	unsigned long long bases, reads, pairs, hapBytes;
+	unsigned int errorFlags;   // bit0: slab overflow, bit1: read outgrew scratch, bit2: too many indel events
+	unsigned int pad;
+};
+
+struct GenParams {
+	DevTables t;
+	const uint32_t* hap2;      // 2-bit codes, 16 bases per word
+	const uint32_t* hapN;      // non-ACGT mask, 32 bases per word
+	const DevBin* bins;
+	const int64_t* emitBase;   // nBins+1 entries
+	int64_t nBins;
+	const uint16_t* riskyAttempt;
+	const char* names;
+	uint64_t seed;
+	int64_t emitLo, emitHi;    // emitted-pair index range of this batch
+	const int32_t* tileStartBin;
+	int nTiles;
+	unsigned long long* tileState;
+	unsigned int* ticket;
+	uint8_t* out1; uint8_t* out2;
+	unsigned long long cap1, cap2;
+	BatchResult* result;
+};
+
+}  // namespace ssc

@@ -1,0 +1,33 @@
+// kernels.h -- launch interface between the host runtime (api.cu) and kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "device_types.h"
+
+#define GEN_WARPS 16
+#define GEN_THREADS (GEN_WARPS * 32)
+#define GEN_PPW 2                                 /* pairs per warp per tile */
+#define GEN_TILE_PAIRS (GEN_WARPS * GEN_PPW)
+
+namespace ssc {
+
+struct GenVariant {
+	int nch;        // chunks of 32 cycles held in registers (5: RL <= 160, 10: RL <= 320)
+	bool k3;        // K == 3 fast context indexing with the substitution tables in shared memory
+	bool qsmem;     // quality tables in shared memory
+	bool fp64;      // FP64 linear-search ground truth
+	size_t smemBytes;
+	bool ok;
+};
+
+GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit);
+cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, cudaStream_t stream);
+cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, uint32_t* hap2, uint32_t* hapN,
+                        const int8_t* lut, cudaStream_t stream);
+cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, int nBins, uint64_t seed,
+                          uint16_t* riskyAttempt, int32_t* emitted, cudaStream_t stream);
+cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int nTiles, int32_t* tileStartBin,
+                          cudaStream_t stream);
+
+}  // namespace ssc

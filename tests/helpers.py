@@ -1,0 +1,140 @@
+"""Shared test plumbing: seeded scenarios run through the Philox-instrumented reference."""
+import glob
+import os
+import subprocess
+
+from simuscop_b200 import planfile, synth, testdata
+from simuscop_b200.paths import REF_PHILOX
+
+# name -> dict(lengths, names, profile, layout, coverage, insertSize, extras)
+SCENARIOS = {
+    # paired-end XTen, N runs and lower-case stretches
+    "pe_xten": dict(lengths=[300000, 120000], profile="XTen", layout="PE", coverage=5, insertSize=300,
+                    n_runs=2, lower_runs=2),
+    # single-end GAIIx (both strands, fragment = bin length)
+    "se_gaiix": dict(lengths=[200000], profile="GAIIx", layout="SE", coverage=3, insertSize=250, n_runs=1),
+    # tiny chromosomes: tail bin shorter than RL (abandon after 1000 fails), chromosome shorter than the insert
+    "pe_tiny": dict(lengths=[1040, 300, 5200], profile="HiSeq2500", layout="PE", coverage=60, insertSize=200),
+    # variations: CNV gain/loss, SNV, insertion, deletion, SNPs
+    "pe_variants": dict(lengths=[2600000], names=["chr20"], profile="HiSeq2000", layout="PE", coverage=2,
+                        insertSize=250, variation=True, snp=True, n_runs=2),
+    # capture targets
+    "pe_wes": dict(lengths=[900000], names=["chr20"], profile="HiSeq2500", layout="PE", coverage=20,
+                   insertSize=200, target=True),
+    # four populations mixed by two abundance rows, single-end
+    "se_tumor": dict(lengths=[1500000], names=["chr20"], profile="GAIIx", layout="SE", coverage=2,
+                     insertSize=250, tumor=True),
+}
+
+VARIATION_SMALL = """\
+i\ttest\tchr20\t450010\ttcgagtcg\thomo
+i\ttest\tchr20\t1100010\ttcgagtc\thomo
+i\ttest\tchr20\t1200010\ttcgagt\thet
+d\ttest\tchr20\t460010\t8\thomo
+d\ttest\tchr20\t1300010\t12\thet
+d\ttest\tchr20\t1400010\t5\thet
+s\ttest\tchr20\t500010\tA\tC\thomo
+s\ttest\tchr20\t600010\tG\tT\thet
+s\ttest\tchr20\t700010\tC\tA\thet
+c\ttest\tchr20\t800001\t1200000\t3\t2
+c\ttest\tchr20\t1600001\t1900000\t1\t1
+c\ttest\tchr20\t2000001\t2400000\t4\t2
+"""
+
+VARIATION_TUMOR = """\
+i\tclone1\tchr20\t450010\ttcgagtcg\thomo
+i\tclone2\tchr20\t450010\ttcgagtcg\thet
+d\tclone3\tchr20\t460010\t8\thomo
+s\tclone1\tchr20\t500010\tA\tC\thomo
+s\tclone2\tchr20\t600010\tG\tT\thet
+s\tclone4\tchr20\t700010\tC\tA\thet
+c\tclone1\tchr20\t200001\t600000\t3\t2
+c\tclone2\tchr20\t700001\t900000\t1\t1
+c\tclone3\tchr20\t1000001\t1400000\t4\t3
+c\tclone4\tchr20\t100001\t300000\t5\t3
+"""
+
+
+def build_scenario(name, workdir, seed=7):
+    """Writes genome/config for SCENARIOS[name]; returns dict(cfg=..., dir=..., seed=...)."""
+    sc = SCENARIOS[name]
+    d = os.path.join(workdir, name)
+    os.makedirs(d, exist_ok=True)
+    data = testdata.materialize(os.path.join(workdir, "data"))
+    synth.make_genome(os.path.join(d, "ref.fa"), sc["lengths"], seed=20, names=sc.get("names"),
+                      n_runs=sc.get("n_runs", 0), lower_runs=sc.get("lower_runs", 0), run_len=300)
+    kw = dict(ref=os.path.join(d, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[sc["profile"]]),
+              layout=sc["layout"], coverage=sc["coverage"], insertSize=sc["insertSize"], threads=1, verbose=0,
+              name="test")
+    if sc.get("variation"):
+        with open(os.path.join(d, "variations.txt"), "w") as f:
+            f.write(VARIATION_SMALL)
+        kw["variation"] = os.path.join(d, "variations.txt")
+    if sc.get("snp"):
+        # SNPs of the shipped file that fall inside the synthetic chromosome
+        with open(os.path.join(data, "snp.txt")) as f, open(os.path.join(d, "snp.txt"), "w") as g:
+            for line in f:
+                p = line.split("\t")
+                if len(p) >= 3 and int(p[2]) <= sc["lengths"][0]:
+                    g.write(line)
+        kw["snp"] = os.path.join(d, "snp.txt")
+    if sc.get("target"):
+        with open(os.path.join(data, "exon_regions.bed")) as f, open(os.path.join(d, "targets.bed"), "w") as g:
+            for line in f:
+                p = line.split("\t")
+                if len(p) >= 3 and int(p[2]) + 60 <= sc["lengths"][0]:
+                    g.write(line)
+        kw["target"] = os.path.join(d, "targets.bed")
+    if sc.get("tumor"):
+        with open(os.path.join(d, "variations.txt"), "w") as f:
+            f.write(VARIATION_TUMOR)
+        with open(os.path.join(d, "abundance.txt"), "w") as f:
+            f.write("1.0\t0\t0\t0\n0.3\t0.25\t0.35\t0.1\n")
+        kw["variation"] = os.path.join(d, "variations.txt")
+        kw["abundance"] = os.path.join(d, "abundance.txt")
+        kw["name"] = "clone1,clone2,clone3,clone4"
+    return dict(dir=d, kw=kw, seed=seed, name=name)
+
+
+def run_reference_philox(scn, tag="ref"):
+    """Runs the instrumented reference; returns (list of plan paths, sorted list of fastq paths)."""
+    d = scn["dir"]
+    out = os.path.join(d, "out_" + tag)
+    cfg = os.path.join(d, "cfg_%s.txt" % tag)
+    synth.write_config(cfg, output=out, **scn["kw"])
+    for f in glob.glob(os.path.join(d, "plan_%s.*.plan" % tag)):
+        os.remove(f)
+    env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_DUMP_PLAN=os.path.join(d, "plan_" + tag))
+    r = subprocess.run([REF_PHILOX, cfg], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    plans = sorted(glob.glob(os.path.join(d, "plan_%s.*.plan" % tag)), key=lambda p: int(p.split(".")[-2]))
+    return plans, out
+
+
+def sample_files(out, plan, index, scn):
+    """FASTQ files the reference wrote for plan/sample `index` (Genome.cpp:857-866, 899-929)."""
+    if scn["kw"].get("abundance"):
+        with open(scn["kw"]["abundance"]) as f:
+            rows = [l.split("\t") for l in f.read().splitlines() if l]
+        names = scn["kw"]["name"].split(",")
+        fn = "+".join("%s_%.3f" % (n, float(p)) for n, p in zip(names, rows[index]))
+    else:
+        fn = scn["kw"]["name"].split(",")[0]
+    if plan.paired:
+        return os.path.join(out, fn + "_1.fq"), os.path.join(out, fn + "_2.fq")
+    return os.path.join(out, fn + ".fq"), None
+
+
+def read_file(p):
+    if p is None:
+        return b""
+    with open(p, "rb") as f:
+        return f.read()
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return i
+    return n if len(a) != len(b) else -1
