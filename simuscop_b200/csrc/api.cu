@@ -65,6 +65,7 @@ struct ssc_handle {
 	// options
 	int64_t batchPairs = 1 << 20;
 	bool fp64 = false;
+	bool forceGeneric = false;
 
 	// profile
 	bool haveProfile = false;
@@ -104,6 +105,9 @@ struct ssc_handle {
 	DevBuf<int32_t> d_tileStart[2];
 	DevBuf<unsigned long long> d_tileState[2];
 	DevBuf<unsigned int> d_ticket[2];
+	uint8_t* d_slots[2] = {nullptr, nullptr};   // pass-1 scratch of the fast kernel (one set, stream ordered)
+	DevBuf<uint32_t> d_slotLens;
+	DevBuf<unsigned int> d_ticket2;
 	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
 	ssc::BatchResult* h_result[2] = {nullptr, nullptr};
 
@@ -112,9 +116,15 @@ struct ssc_handle {
 
 namespace {
 
+bool use_fast(const ssc_handle* h, bool* qsmem, size_t* smemBytes) {
+	if (h->fp64 || h->forceGeneric) return false;
+	return ssc::fast_supported(h->dt, h->smemLimit, qsmem, smemBytes);
+}
+
+
 int ensure_batch_resources(ssc_handle* h, bool needHost) {
 	int64_t pairs = std::min<int64_t>(h->batchPairs, std::max<int64_t>(h->emittedPairs, 1));
-	pairs = ((pairs + GEN_TILE_PAIRS - 1) / GEN_TILE_PAIRS) * GEN_TILE_PAIRS;
+	pairs = ((pairs + GEN_TILE_PAIRS - 1) / GEN_TILE_PAIRS) * GEN_TILE_PAIRS;   // multiple of both tile sizes
 	uint64_t cap = (uint64_t)pairs * (uint64_t)h->maxRecBytes + 4096;
 	if (cap >= (1ull << 31)) {
 		pairs = (int64_t)(((1ull << 31) - 8192) / (uint64_t)h->maxRecBytes);
@@ -130,8 +140,12 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 				if (h->h_out[b][f]) cudaFreeHost(h->h_out[b][f]);
 				h->d_out[b][f] = nullptr; h->h_out[b][f] = nullptr;
 			}
+		for (int f = 0; f < 2; f++) { if (h->d_slots[f]) cudaFree(h->d_slots[f]); h->d_slots[f] = nullptr; }
 		h->slabPairs = pairs; h->slabCap = cap;
-		int nTiles = (int)(pairs / GEN_TILE_PAIRS);
+		for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_slots[f], (size_t)pairs * FG_SLOT + 64));
+		CK(h->d_slotLens.alloc((size_t)pairs));
+		CK(h->d_ticket2.alloc(1));
+		int nTiles = (int)(pairs / 16) + 2;   // enough for every kernel's tile size
 		for (int b = 0; b < 2; b++) {
 			for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_out[b][f], cap));
 			CK(h->d_tileStart[b].alloc(nTiles));
@@ -157,12 +171,15 @@ int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
 }
 
 int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
-	int nTiles = (int)((emitHi - emitLo + GEN_TILE_PAIRS - 1) / GEN_TILE_PAIRS);
+	bool qsmem = false; size_t fastSmem = 0;
+	const bool fast = use_fast(h, &qsmem, &fastSmem);
+	const int tp = fast ? FG_WORKERS : GEN_TILE_PAIRS;
+	int nTiles = (int)((emitHi - emitLo + tp - 1) / tp);
 	cudaStream_t s = h->compute;
 	CK(cudaMemsetAsync(h->d_tileState[buf].p, 0, sizeof(unsigned long long) * nTiles, s));
 	CK(cudaMemsetAsync(h->d_ticket[buf].p, 0, sizeof(unsigned int), s));
 	CK(cudaMemsetAsync(h->d_result[buf], 0, sizeof(ssc::BatchResult), s));
-	CK(ssc::launch_locate(h->d_emitBase.p, h->nDevBins, emitLo, nTiles, h->d_tileStart[buf].p, s));
+	CK(ssc::launch_locate(h->d_emitBase.p, h->nDevBins, emitLo, tp, nTiles, h->d_tileStart[buf].p, s));
 	ssc::GenParams P;
 	P.t = h->dt;
 	P.hap2 = h->d_hap2.p; P.hapN = h->d_hapN.p;
@@ -174,10 +191,19 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	P.out1 = h->d_out[buf][0]; P.out2 = h->d_out[buf][1];
 	P.cap1 = h->slabCap; P.cap2 = h->slabCap;
 	P.result = h->d_result[buf];
-	ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
-	if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
 	int grid = std::min(nTiles, h->smCount);
-	CK(ssc::launch_generate(P, v, grid, s));
+	if (fast) {
+		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
+		P.dense1 = P.out1; P.dense2 = P.out2;
+		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
+		P.slotLens = h->d_slotLens.p;
+		CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s));
+		h->stats.launches += 1;
+	} else {
+		ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
+		if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
+		CK(ssc::launch_generate(P, v, grid, s));
+	}
 	CK(cudaMemcpyAsync(h->h_result[buf], h->d_result[buf], sizeof(ssc::BatchResult), cudaMemcpyDeviceToHost, s));
 	h->stats.launches += 2;
 	h->stats.gen_launches += 1;
@@ -246,6 +272,7 @@ int ssc_destroy(ssc_handle* h) {
 		}
 		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
 		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
+		if (h->d_slots[b]) cudaFree(h->d_slots[b]);
 		if (h->d_result[b]) cudaFree(h->d_result[b]);
 		if (h->h_result[b]) cudaFreeHost(h->h_result[b]);
 		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();
@@ -258,6 +285,7 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
 	h->d_hap2.release(); h->d_hapN.release();
+	h->d_slotLens.release(); h->d_ticket2.release();
 	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
 	if (h->evStart) cudaEventDestroy(h->evStart);
 	if (h->evStop) cudaEventDestroy(h->evStop);
@@ -274,6 +302,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 		h->batchPairs = value;
 		return SSC_OK;
 	}
+	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
 	if (!strcmp(key, "fp64_search")) {
 		if (h->havePlan) return fail(SSC_ERR_STATE, "fp64_search must be set before ssc_set_plan");
 		h->fp64 = value != 0;
@@ -341,7 +370,7 @@ int ssc_genome_reserve(ssc_handle* h, uint64_t total_bases) {
 	if (!h) return fail(SSC_ERR_INVALID, "null handle");
 	if (!h->haveProfile) return fail(SSC_ERR_STATE, "ssc_set_profile must precede ssc_genome_reserve (codes follow the profile's base order)");
 	CK(cudaSetDevice(h->device));
-	uint64_t groups = (total_bases + 31) / 32 + 2;
+	uint64_t groups = (total_bases + SSC_GPAD + 31) / 32 + 2;
 	CK(h->d_hap2.alloc(groups * 2 + 64));
 	CK(h->d_hapN.alloc(groups + 64));
 	CK(cudaMemsetAsync(h->d_hap2.p, 0, (groups * 2 + 64) * 4, h->compute));
@@ -368,7 +397,7 @@ int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* fi
 		CK(cudaEventSynchronize(h->evStage[k]));           // staging buffer k free again
 		memcpy(h->h_stage[k], ascii + done, chunk);
 		CK(cudaMemcpyAsync(h->d_stage[k], h->h_stage[k], chunk, cudaMemcpyHostToDevice, h->compute));
-		CK(ssc::launch_pack(h->d_stage[k], chunk, h->genomeSize + done, h->d_hap2.p, h->d_hapN.p, h->d_lut.p, h->compute));
+		CK(ssc::launch_pack(h->d_stage[k], chunk, SSC_GPAD + h->genomeSize + done, h->d_hap2.p, h->d_hapN.p, h->d_lut.p, h->compute));
 		CK(cudaEventRecord(h->evStage[k], h->compute));
 		h->stats.launches += 1;
 		h->stats.h2d_bytes += chunk;
@@ -433,7 +462,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 			if (paired && t.nIsize == 0 && t.fixedInsert < RL) risky = true;
 			if (risky) {
 				ssc::CensusBin c;
-				c.hap_base = b.hap_base; c.contig_end = b.contig_end; c.plan_base = pb[i];
+				c.hap_base = b.hap_base + SSC_GPAD; c.contig_end = b.contig_end + SSC_GPAD; c.plan_base = pb[i];
 				c.spos = b.spos; c.epos = b.epos; c.planned = (int32_t)n; c.risky_base = (int32_t)riskyTotal;
 				if (riskyTotal + n > 0x7fffffff) return fail(SSC_ERR_INVALID, "too many pairs in bins that can fail");
 				riskyBase[i] = (int32_t)riskyTotal;
@@ -477,7 +506,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 				if (bins[i].segment != sIdx) return fail(SSC_ERR_INVALID, "bin %lld does not belong to segment %lld", (long long)i, (long long)sIdx);
 				if (fragBase + emit[i] > 0x7fffffff) return fail(SSC_ERR_INVALID, "segment %lld: fragment counter overflow", (long long)sIdx);
 				ssc::DevBin d;
-				d.hap_base = bins[i].hap_base; d.contig_end = bins[i].contig_end;
+				d.hap_base = bins[i].hap_base + SSC_GPAD; d.contig_end = bins[i].contig_end + SSC_GPAD;
 				d.plan_base = pb[i]; d.emit_base = eb[i];
 				d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
 				d.frag_base = (int32_t)fragBase;

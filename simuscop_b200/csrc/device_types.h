@@ -68,7 +68,9 @@ struct GenParams {
 	int nTiles;
 	unsigned long long* tileState;
 	unsigned int* ticket;
-	uint8_t* out1; uint8_t* out2;
+	uint8_t* out1; uint8_t* out2;       // generic kernel: final slabs; fast kernel: slot scratch
+	uint8_t* dense1; uint8_t* dense2;   // fast kernel: final slabs (pass 2)
+	uint32_t* slotLens;                 // fast kernel: len1 | len2 << 16 per slot
 	unsigned long long cap1, cap2;
 	BatchResult* result;
 };

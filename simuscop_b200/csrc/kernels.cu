@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generate_kernel(const GenParam
 			frag_attempt<FP64>(t, s_isizeT, s_isizeSym, P.seed, pair, attempt, bin.hap_base, bin.contig_end,
 			                   bin.spos, bin.epos, pos, flen, strandWord);
 			const int64_t fstart = bin.hap_base + pos;
-			const uint32_t posmod = (uint32_t)((unsigned long long)pos % bin.segsize);
+			const uint32_t posmod = (uint32_t)pos % bin.segsize;
 			const bool seReverse = (!t.paired) && ((strandWord >> 31) != 0);   // randomInteger(0,2) != 0
 			accPairs += 1;
 			accHap += (unsigned long long)((flen + 3) / 4 + (flen + 7) / 8);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generate_kernel(const GenParam
 				if (lane == 0) { stage[H + m] = '\n'; stage[H + m + 1] = '+'; stage[H + m + 2] = '\n'; stage[H + 2 * m + 3] = '\n'; }
 
 				// ---- phase C: substitution + quality at output position j
-				const uint32_t inv = (m > 1) ? (uint32_t)((0x100000000ull + (uint32_t)m - 1) / (uint32_t)m) : 0xffffffffu;
+				const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
 				const int chunksM = (m + 31) >> 5;
 				const uint4* subM = subTab + ((mate == 1 && t.useCdf2) ? t.nSub : 0);
 				const double* fsub = (mate == 1 && t.useCdf2) ? t.f_sub2 : t.f_sub1;
@@ -639,7 +639,7 @@ static cudaError_t launch_variant(const GenParams& P, int grid, size_t smemBytes
 
 GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit) {
 	GenVariant v;
-	v.nch = (t.RL <= 160) ? 5 : 10;
+	v.nch = 10;
 	v.fp64 = fp64;
 	v.k3 = (t.K == 3) && !fp64;
 	v.qsmem = false;
@@ -649,10 +649,9 @@ GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit) {
 		int nSub = k3 ? t.nSub * (t.useCdf2 ? 2 : 1) : 0;
 		int nQ = qs ? t.nQualRows * t.qualPitch : 0;
 		int a = fp64 ? 0 : t.nIsize, b = fp64 ? 0 : t.nInsLen, c = fp64 ? 0 : t.nDelLen;
-		return v.nch == 5 ? smem_layout<5>(nSub, nQ, a, b, c).total : smem_layout<10>(nSub, nQ, a, b, c).total;
+		return smem_layout<10>(nSub, nQ, a, b, c).total;
 	};
 	if (fp64) { v.smemBytes = size(false, false); return v; }
-	if (v.nch == 5 && v.k3 && size(true, true) <= smemLimit) { v.qsmem = true; v.smemBytes = size(true, true); return v; }
 	if (v.k3 && size(true, false) <= smemLimit) { v.smemBytes = size(true, false); return v; }
 	v.k3 = false;
 	v.smemBytes = size(false, false);
@@ -661,13 +660,7 @@ GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit) {
 }
 
 cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, cudaStream_t stream) {
-	if (v.fp64) return v.nch == 5 ? launch_variant<5, false, false, true>(P, grid, v.smemBytes, stream)
-	                              : launch_variant<10, false, false, true>(P, grid, v.smemBytes, stream);
-	if (v.nch == 5) {
-		if (v.k3 && v.qsmem) return launch_variant<5, true, true, false>(P, grid, v.smemBytes, stream);
-		if (v.k3) return launch_variant<5, true, false, false>(P, grid, v.smemBytes, stream);
-		return launch_variant<5, false, false, false>(P, grid, v.smemBytes, stream);
-	}
+	if (v.fp64) return launch_variant<10, false, false, true>(P, grid, v.smemBytes, stream);
 	if (v.k3) return launch_variant<10, true, false, false>(P, grid, v.smemBytes, stream);
 	return launch_variant<10, false, false, false>(P, grid, v.smemBytes, stream);
 }
@@ -692,12 +685,12 @@ cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, 
 	return cudaGetLastError();
 }
 
-cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int nTiles, int32_t* tileStartBin,
+cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int tilePairs, int nTiles, int32_t* tileStartBin,
                           cudaStream_t stream) {
 	if (nTiles == 0) return cudaSuccess;
 	int threads = 256;
 	int blocks = (nTiles + threads - 1) / threads;
-	locate_kernel<<<blocks, threads, 0, stream>>>(emitBase, nBins, emitLo, GEN_TILE_PAIRS, nTiles, tileStartBin);
+	locate_kernel<<<blocks, threads, 0, stream>>>(emitBase, nBins, emitLo, tilePairs, nTiles, tileStartBin);
 	return cudaGetLastError();
 }
 

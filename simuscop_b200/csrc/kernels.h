@@ -10,6 +10,11 @@
 #define GEN_PPW 2                                 /* pairs per warp per tile */
 #define GEN_TILE_PAIRS (GEN_WARPS * GEN_PPW)
 
+#define FG_WORKERS 24                             /* independent warps per CTA of the fast kernel (one pair each) */
+#define FG_THREADS (FG_WORKERS * 32)
+#define FG_SLOT 640                               /* bytes of HBM scratch per record (>= 96 + 2*256 + 4) */
+#define SSC_GPAD 64                               /* zero bases in front of the haplotype store */
+
 namespace ssc {
 
 struct GenVariant {
@@ -23,11 +28,13 @@ struct GenVariant {
 
 GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit);
 cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, cudaStream_t stream);
+bool fast_supported(const DevTables& t, int smemLimit, bool* qsmem, size_t* smemBytes);
+cudaError_t launch_generate_fast(const GenParams& P, bool qsmem, size_t smemBytes, int grid, int smCount, cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, uint32_t* hap2, uint32_t* hapN,
                         const int8_t* lut, cudaStream_t stream);
 cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, int nBins, uint64_t seed,
                           uint16_t* riskyAttempt, int32_t* emitted, cudaStream_t stream);
-cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int nTiles, int32_t* tileStartBin,
+cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int tilePairs, int nTiles, int32_t* tileStartBin,
                           cudaStream_t stream);
 
 }  // namespace ssc
