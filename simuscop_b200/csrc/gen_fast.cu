@@ -24,6 +24,12 @@
 #include "kernels.h"
 #include "philox.cuh"
 
+#ifdef PHILOX_UNROLL
+static constexpr int SSC_PHILOX_UNROLL = PHILOX_UNROLL;
+#else
+static constexpr int SSC_PHILOX_UNROLL = 2;   // rounds per loop trip: keeps the hot loop inside the instruction cache
+#endif
+
 namespace ssc {
 
 #define ST_A (1ull << 62)
@@ -98,7 +104,7 @@ __device__ __forceinline__ void philox_chunks(uint32_t pc0, uint32_t pc1, uint32
                                               uint32_t (&o0)[NCH], uint32_t (&o1)[NCH], uint32_t (&o2)[NCH], uint32_t (&o3)[NCH]) {
 #pragma unroll
 	for (int c = 0; c < NCH; c++) { o0[c] = pc0; o1[c] = pc1; o2[c] = pc2; o3[c] = base3 + 32u * c; }
-#pragma unroll
+#pragma unroll (SSC_PHILOX_UNROLL)
 	for (int r = 0; r < 10; r++) {
 #pragma unroll
 		for (int c = 0; c < NCH; c++) {
@@ -203,7 +209,7 @@ __device__ __forceinline__ uint32_t window_code(const WarpCtx& w, int relBase /*
 // Slow path of Profile::predict (a read with at least one indel candidate): compact, not unrolled.
 // evbits: per lane, bit 2c = insertion test hit at cycle 32c+lane, bit 2c+1 = deletion test hit.
 // Writes bases/quals into stage[H ..]; returns m.
-__device__ __noinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int mate, bool rev, int relFirst,
+__device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int mate, bool rev, int relFirst,
                                       uint8_t* stage, int H, unsigned int* errorFlags, const uint32_t* xsave, int nSaved) {
 	const int RL = w.RL, lane = w.lane;
 	const int chunksRL = (RL + 31) >> 5;

@@ -10,7 +10,9 @@
 #define GEN_PPW 2                                 /* pairs per warp per tile */
 #define GEN_TILE_PAIRS (GEN_WARPS * GEN_PPW)
 
+#ifndef FG_WORKERS
 #define FG_WORKERS 24                             /* independent warps per CTA of the fast kernel (one pair each) */
+#endif
 #define FG_THREADS (FG_WORKERS * 32)
 #define FG_SLOT 640                               /* bytes of HBM scratch per record (>= 96 + 2*256 + 4) */
 #define SSC_GPAD 64                               /* zero bases in front of the haplotype store */
