@@ -1,0 +1,455 @@
+// host_plan.cpp -- segmentation, haplotype construction, GC-weighted read plan, and streaming of
+// one output sample into the device handle (haplotype store + bins) through the C ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "host.h"
+
+namespace sschost {
+
+// randomInteger, lib/mydefine/MyDefine.cpp:192-194 (libc rand(), seeded in begin_plan)
+long Job::rand_int(long start, long end) {
+	return (long)(start + (end - start) * (rand() / (RAND_MAX + 1.0)));
+}
+
+// Genome::divideSegment, lib/genome/Genome.cpp:741-763
+void Job::divide_segment(const std::string& popu, const std::string& chr, long s, long e, int CN, int mCN, int& idx) {
+	const unsigned int segMax = 1000000;
+	std::vector<Segment>& v = segs[popu][chr];
+	auto make = [&](long a, long b) {
+		Segment g;
+		g.idx = idx++; g.chr = chr; g.start = a; g.end = b; g.CN = CN; g.mCN = mCN;
+		auto it = targets.find(chr);                         // Segment::initTargets, Segment.cpp:67-79
+		if (!targets.empty() && it != targets.end())
+			for (size_t i = 0; i < it->second.size(); i++) {
+				long ts = it->second[i].spos, te = it->second[i].epos;
+				if ((ts >= a && ts <= b) || (te >= a && te <= b) || (ts < a && te > b)) g.targetIdx.push_back((int)i);
+			}
+		v.push_back(g);
+	};
+	long size = e - s + 1;
+	int n = (int)(size / segMax);
+	unsigned int m = (unsigned int)(size - (long)n * segMax);
+	for (int i = 0; i < n; i++) {
+		if (i == n - 1 && m < segMax / 2) { make(s, e); s = e + 1; }
+		else { make(s, s + segMax - 1); s += segMax; }
+	}
+	if (s <= e) make(s, e);
+}
+
+// Genome::generateSegments, lib/genome/Genome.cpp:634-682
+void Job::generate_segments() {
+	int ploidy = cfg.num["ploidy"];
+	int mCN = (int)ceil((float)ploidy / 2);
+	if (!targets.empty()) {
+		chroms.clear();
+		for (auto& kv : targets) chroms.push_back(kv.first);
+	}
+	for (auto& popu : cfg.popu) {
+		for (auto& chr : chroms) {
+			int idx = 0;
+			std::vector<Cnv>& cv = cnvs[popu][chr];
+			long segStart = 1;
+			long chrLen = chrom_len(chr);
+			segs[popu][chr];
+			for (auto c : cv) {
+				if (segStart > chrLen) break;
+				c.epos = std::min(c.epos, chrLen);
+				if (segStart < c.spos) divide_segment(popu, chr, segStart, c.spos - 1, ploidy, mCN, idx);
+				divide_segment(popu, chr, c.spos, c.epos, (int)c.cn, (int)c.mcn, idx);
+				segStart = c.epos + 1;
+			}
+			if (segStart <= chrLen) divide_segment(popu, chr, segStart, chrLen, ploidy, mCN, idx);
+		}
+	}
+}
+
+// Segment::generateSegSequences, lib/segment/Segment.cpp:124-460
+void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<std::string>& haps) {
+	const int ploidy = cfg.num["ploidy"];
+	haps.assign(ploidy, std::string());
+	if (seg.CN == 0) die(1, "ERROR: copy number 0 segments are not supported (" + popu + " " + seg.chr + ":" + std::to_string(seg.start) + ")");
+	const std::string& chrSeq = fasta.chromosome(seg.chr);
+	std::string ref = chrSeq.substr((size_t)(seg.start - 1), (size_t)seg.refSize());
+	const unsigned int refSize = (unsigned int)ref.size();
+	const int CN = seg.CN, mCN = seg.mCN;
+	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
+	if (seg.mIndx.empty()) {
+		if (CN < ploidy) {
+			for (int i = 0; i < CN; i++)
+				while (true) {
+					int j = (int)rand_int(0, ploidy);
+					if (std::find(seg.seqReps.begin(), seg.seqReps.end(), j) == seg.seqReps.end()) { seg.seqReps.push_back(j); break; }
+				}
+			for (int i = 0; i < mCN; i++) seg.mIndx.push_back(seg.seqReps[i]);
+		} else {
+			for (int i = 0; i < ploidy; i++) seg.seqReps.push_back(1);
+			int n = CN - ploidy;
+			int k = (int)rand_int(0, ploidy);
+			int i;
+			for (i = n; i >= 0; i--) {
+				if (seg.seqReps[k] + i == mCN) { seg.seqReps[k] += i; seg.mIndx.push_back(k); break; }
+				else if (seg.seqReps[k] + i == CN - mCN) {
+					seg.seqReps[k] += i;
+					for (int j = 0; j < ploidy; j++) if (j != k) seg.mIndx.push_back(j);
+					break;
+				}
+			}
+			if (i >= 0) {
+				n -= i;
+				while (n > 0) { int j = (int)rand_int(0, ploidy); if (j != k) { seg.seqReps[j]++; n--; } }
+			} else {
+				while (n > 0) { int j = (int)rand_int(0, ploidy); seg.seqReps[j]++; n--; }
+				for (int j = 0; j < ploidy; j++) seg.mIndx.push_back(j);
+			}
+		}
+	}
+	if (CN < ploidy) {
+		for (int i = 0; i < ploidy; i++)
+			if (std::find(seg.seqReps.begin(), seg.seqReps.end(), i) != seg.seqReps.end()) haps[i] = ref;
+	} else {
+		for (int i = 0; i < ploidy; i++) {
+			haps[i].reserve((size_t)refSize * seg.seqReps[i] + 64);
+			for (int j = 0; j < seg.seqReps[i]; j++) haps[i] += ref;
+		}
+	}
+	auto poke = [&](std::string& h, int sindx, char c) {
+		unsigned int len = (unsigned int)h.length();
+		for (unsigned int t = 0; t < len / refSize; t++) h[sindx + t * refSize] = c;
+	};
+	// SNPs: heterozygous, alternating between the major set and its complement (Segment.cpp:233-265)
+	int k = 0;
+	auto sit = snps.find(seg.chr);
+	if (sit != snps.end())
+		for (const Snp& s : sit->second) {
+			if (s.pos >= seg.start && s.pos <= seg.end) {
+				int sindx = (int)(s.pos - seg.start);
+				for (int j = 0; j < ploidy; j++) if ((k == 0) == inM(j)) poke(haps[j], sindx, s.nucleotide);
+				k = (k + 1) % 2;
+			}
+		}
+	// SNVs (Segment.cpp:267-311)
+	k = 0;
+	for (const Snv& s : snvs[popu][seg.chr]) {
+		if (s.pos >= seg.start && s.pos <= seg.end) {
+			int sindx = (int)(s.pos - seg.start);
+			if (!s.het) for (int j = 0; j < ploidy; j++) poke(haps[j], sindx, s.alt);
+			else {
+				for (int j = 0; j < ploidy; j++) if ((k == 0) == inM(j)) poke(haps[j], sindx, s.alt);
+				k = (k + 1) % 2;
+			}
+		}
+	}
+	// insertions (Segment.cpp:313-370)
+	std::vector<std::map<int, int>> insMap(ploidy), delMap(ploidy);
+	std::vector<int> insLens(ploidy, 0), delLens(ploidy, 0);
+	k = 0;
+	for (const Ins& in : inss[popu][seg.chr]) {
+		if (in.pos >= seg.start && in.pos <= seg.end) {
+			int sindx = (int)(in.pos + 1 - seg.start);
+			int len = (int)in.seq.length();
+			for (int j = 0; j < ploidy; j++) {
+				if (in.het && ((k == 0 && !inM(j)) || (k == 1 && inM(j)))) continue;
+				int offset = 0;
+				for (auto& kv : insMap[j]) if (kv.first <= sindx) offset += kv.second;
+				std::string& h = haps[j];
+				int n = (int)(h.length() / (refSize + insLens[j]));
+				for (int t = 0; t < n; t++) h.insert((size_t)(sindx + offset + t * (refSize + insLens[j] + len)), in.seq);
+				insLens[j] += len;
+				insMap[j].insert(std::make_pair(sindx, len));
+			}
+			if (in.het) k = (k + 1) % 2;
+		}
+	}
+	// deletions (Segment.cpp:372-444)
+	k = 0;
+	for (const Del& d : dels[popu][seg.chr]) {
+		if (d.pos >= seg.start && d.pos <= seg.end) {
+			int sindx = (int)(d.pos - seg.start);
+			for (int j = 0; j < ploidy; j++) {
+				if (d.het && ((k == 0 && !inM(j)) || (k == 1 && inM(j)))) continue;
+				int offset = 0;
+				for (auto& kv : insMap[j]) if (kv.first <= sindx) offset += kv.second;
+				for (auto& kv : delMap[j]) if (kv.first <= sindx) offset -= kv.second;
+				if (sindx + offset < 0) continue;
+				std::string& h = haps[j];
+				int n = (int)(h.length() / (refSize + insLens[j] - delLens[j]));
+				for (int t = 0; t < n; t++) h.erase((size_t)(sindx + offset + t * (refSize + insLens[j] - delLens[j] - d.len)), (size_t)d.len);
+				delLens[j] += d.len;
+				delMap[j].insert(std::make_pair(sindx, d.len));
+			}
+			if (d.het) k = (k + 1) % 2;
+		}
+	}
+	for (auto& h : haps) std::transform(h.begin(), h.end(), h.begin(), [](unsigned char c) { return (char)toupper(c); });
+}
+
+// calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303
+static int gc_percent(const char* s, size_t n) {
+	if (n == 0) return 0;
+	int gc = 0, nn = 0;
+	for (size_t i = 0; i < n; i++) {
+		char c = s[i];
+		if (c == 'G' || c == 'C') gc++;
+		else if (c == 'N') nn++;
+	}
+	if (nn > 0) return -1;
+	return 100 * gc / (int)(n - nn);
+}
+
+// Segment::getWeightedLength, lib/segment/Segment.cpp:550-641
+double Job::weighted_length(Segment& seg, const std::string& popu) {
+	double wl = 0;
+	if (seg.weighted) {
+		for (auto& b : seg.bins) wl += b.weight;
+		return wl;
+	}
+	const int ploidy = cfg.num["ploidy"];
+	const unsigned int fragSize = 1000;
+	std::vector<std::string> haps;
+	build_haplotypes(seg, popu, haps);
+	if (targets.empty()) {
+		for (int i = 0; i < ploidy; i++) {
+			const std::string& p = haps[i];
+			if (p.empty()) continue;
+			size_t len = p.length();
+			int k = (int)(len / fragSize);
+			for (int j = 0; j < k; j++) {
+				long spos = (long)j * fragSize, epos = (long)(j + 1) * fragSize - 1;
+				int gc = gc_percent(p.data() + spos, fragSize);
+				double w = prof.gc_factor(gc) / fragSize;
+				seg.bins.push_back(Bin{spos, epos, i, w, 0});
+				wl += w;
+			}
+			if ((size_t)k * fragSize < len) {
+				long spos = (long)k * fragSize;
+				int gc = gc_percent(p.data() + spos, len - (size_t)spos);
+				double w = prof.gc_factor(gc) * (len - (size_t)spos) / (fragSize * fragSize);
+				seg.bins.push_back(Bin{spos, (long)len - 1, i, w, 0});
+				wl += w;
+			}
+		}
+	} else if (!seg.targetIdx.empty()) {
+		const std::vector<Target>& tg = targets[seg.chr];
+		for (int i = 0; i < ploidy; i++) {
+			const std::string& p = haps[i];
+			if (p.empty()) continue;
+			int n = ((int)seg.seqReps.size() < ploidy) ? 1 : seg.seqReps[i];
+			long refLen = (long)(p.length() / n);
+			for (int k = 0; k < n; k++)
+				for (int m : seg.targetIdx) {
+					long spos = std::max(tg[m].spos, seg.start) - seg.start;
+					long epos = std::min(tg[m].epos, seg.start + refLen - 1) - seg.start;
+					long sk = spos + (long)(k * p.length() / n), ek = epos + (long)(k * p.length() / n);
+					int gc = gc_percent(p.data() + sk, ek >= sk ? (size_t)(ek - sk + 1) : 0);
+					double w = prof.gc_factor(gc) * (ek - sk + 1) / (fragSize * fragSize);
+					seg.bins.push_back(Bin{sk, ek, i, w, 0});
+					wl += w;
+				}
+		}
+	} else {
+		seg.bins.push_back(Bin{0, 0, 0, 0.0, 0});
+	}
+	seg.weighted = !seg.bins.empty();
+	return wl;
+}
+
+// Genome::setReadCounts + Segment::setReadCount, lib/genome/Genome.cpp:783-825, lib/segment/Segment.cpp:462-476
+void Job::set_read_counts(const std::string& popu, long nreads) {
+	std::map<std::string, double> chrWL;
+	double WL = 0;
+	for (auto& chr : chroms) {
+		double w = 0;
+		for (auto& sg : segs[popu][chr]) w += weighted_length(sg, popu);
+		WL += w;
+		chrWL[chr] = w;
+	}
+	long cur = 0;
+	for (size_t i = 0; i < chroms.size(); i++) {
+		std::vector<Segment>& v = segs[popu][chroms[i]];
+		double cw = chrWL[chroms[i]];
+		long chrReads = (i + 1 < chroms.size()) ? (long)(nreads * (cw / WL)) : nreads - cur;
+		long sum = 0;
+		for (size_t j = 0; j < v.size(); j++) {
+			long rc;
+			if (j + 1 < v.size()) { rc = (long)((weighted_length(v[j], popu) / cw) * chrReads); sum += rc; }
+			else rc = chrReads - sum;
+			Segment& sg = v[j];
+			double total = weighted_length(sg, popu) + 2.2204e-16;
+			long acc = 0;
+			for (auto& b : sg.bins) { long r = (long)(b.weight * rc / total); b.rc = (int)r; acc += r; }
+			if (acc < rc && !sg.bins.empty()) sg.bins[0].rc += (int)(rc - acc);
+			sg.readCount = rc;
+		}
+		cur += chrReads;
+	}
+}
+
+// head of Genome::yieldReads, lib/genome/Genome.cpp:827-852
+void Job::begin_plan() {
+	if (planSeeded) return;
+	planSeeded = true;
+	reads = target_length() * cfg.num["coverage"] / cfg.num["readLength"];
+	if (cfg.verbose()) std::cerr << "\nNumber of reads to sample: " << reads << std::endl;
+	for (auto& pk : segs) {
+		long sum = 0;
+		for (auto& ck : pk.second)
+			for (auto& sg : ck.second) sum += (long)((unsigned int)(sg.CN * sg.refSize()));
+		acn[pk.first] = (double)sum / genome_length();
+	}
+	if (cfg.verbose()) {
+		std::cerr << (acn.size() > 1 ? "\nAverage copy number of populations: " : "\nAverage copy number: ") << std::endl;
+		for (auto& kv : acn) std::cerr << kv.first << ": " << kv.second << std::endl;
+	}
+	std::cerr << "\n*****Generating samples*****" << std::endl;
+	srand((unsigned)seed);
+	prof.seed_gc(seed);
+}
+
+namespace {
+struct PlanWriter {
+	FILE* fp = nullptr;
+	template <class T> static void app(std::string& s, T v) { s.append((const char*)&v, sizeof(T)); }
+	void rec(int32_t tag, const std::string& body) {
+		int64_t n = (int64_t)body.size();
+		fwrite(&tag, 4, 1, fp); fwrite(&n, 8, 1, fp); fwrite(body.data(), 1, body.size(), fp);
+	}
+};
+}  // namespace
+
+int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int64_t* planned, int64_t* emitted) {
+	begin_plan();
+	const Sample& sm = samples[s];
+	const int ploidy = cfg.num["ploidy"];
+	const bool paired = cfg.paired();
+	// dev == nullptr: plan-only mode (no GPU needed): store offsets are tracked locally, the plan is only dumped
+	ssc_profile_tables pt;
+	prof.fill(&pt, cfg);
+	int rc = dev ? ssc_set_profile(dev, &pt) : 0;
+	if (rc) return rc;
+	uint64_t localSize = 0;
+
+	// populations of this sample and their read budgets (Genome.cpp:868, 931-936)
+	std::vector<std::pair<std::string, long>> pops;
+	if (sm.props.empty()) pops.push_back({cfg.popu[0], reads});
+	else {
+		double w_acn = 0;
+		for (size_t i = 0; i < cfg.popu.size(); i++) w_acn += sm.props[i] * acn[cfg.popu[i]];
+		for (size_t i = 0; i < cfg.popu.size(); i++) {
+			long pr = (long)(reads * sm.props[i] * acn[cfg.popu[i]] / w_acn);   // long * float is a float product in the reference
+			pops.push_back({cfg.popu[i], pr});
+		}
+	}
+
+	PlanWriter pw;
+	if (!dumpPath.empty()) {
+		pw.fp = fopen(dumpPath.c_str(), "wb");
+		if (!pw.fp) die(3, "cannot open " + dumpPath);
+		fwrite("SSCPLAN1", 1, 8, pw.fp);
+		std::string p;
+		int32_t hdr[16] = {prof.N, prof.K, prof.B, prof.Q, prof.minQ, prof.RL, paired ? 1 : 0, prof.useCdf2 ? 1 : 0,
+		                   cfg.num["insertSize"], prof.isizeCdf.empty() ? 0 : prof.minIS, (int32_t)prof.isizeCdf.size(),
+		                   (int32_t)prof.insCdf.size(), (int32_t)prof.delCdf.size(), prof.rows, ploidy, 0};
+		p.append((const char*)hdr, sizeof(hdr));
+		PlanWriter::app<double>(p, prof.insertRate); PlanWriter::app<double>(p, prof.delRate);
+		char b8[8]; memset(b8, 0, 8); strncpy(b8, prof.bases.c_str(), 8); p.append(b8, 8);
+		auto ad = [&](const std::vector<double>& v) { if (!v.empty()) p.append((const char*)v.data(), v.size() * 8); };
+		ad(prof.isizeCdf); ad(prof.insCdf); ad(prof.delCdf); ad(prof.sub1); if (prof.useCdf2) ad(prof.sub2); ad(prof.qual);
+		pw.rec(1, p);
+	}
+
+	// upper bound of the haplotype store of this sample
+	uint64_t reserve = 0;
+	for (auto& pp : pops)
+		for (auto& chr : chroms) {
+			uint64_t insTotal = 0;
+			for (auto& in : inss[pp.first][chr]) insTotal += in.seq.length();
+			for (auto& sg : segs[pp.first][chr]) reserve += (uint64_t)std::max(sg.CN, 1) * ((uint64_t)sg.refSize() + insTotal);
+		}
+	rc = dev ? ssc_genome_reserve(dev, reserve + 1024) : 0;
+	if (rc) return rc;
+
+	std::vector<ssc_bin> bins;
+	std::vector<ssc_segment> segments;
+	std::string names;
+	for (auto& pp : pops) {
+		const std::string& popu = pp.first;
+		set_read_counts(popu, pp.second);
+		for (auto& chr : chroms) {
+			std::vector<Segment>& v = segs[popu][chr];
+			const int32_t nameOff = (int32_t)names.size();
+			const std::string nm = "@" + popu + "#" + chr + "#";
+			names += nm;
+			// materialise the chromosome's haplotypes (Genome.cpp:876-878)
+			std::vector<std::vector<std::string>> haps(v.size());
+			for (size_t k = 0; k < v.size(); k++) build_haplotypes(v[k], popu, haps[k]);
+			if (pw.fp) {
+				std::string u;
+				PlanWriter::app<int32_t>(u, (int32_t)popu.size()); PlanWriter::app<int32_t>(u, (int32_t)chr.size());
+				u += popu; u += chr;
+				pw.rec(2, u);
+			}
+			// contig layout: for every haplotype index, the segments' strings in order
+			std::vector<std::vector<int64_t>> base(v.size(), std::vector<int64_t>(ploidy, -1));
+			std::vector<int64_t> contigEnd(ploidy, 0);
+			for (int h = 0; h < ploidy; h++) {
+				for (size_t k = 0; k < v.size(); k++) {
+					if (haps[k][h].empty()) continue;
+					uint64_t first = localSize;
+					rc = dev ? ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first) : 0;
+					if (rc) return rc;
+					base[k][h] = (int64_t)first;
+					localSize = first + haps[k][h].size();
+				}
+				contigEnd[h] = (int64_t)localSize;
+			}
+			for (size_t k = 0; k < v.size(); k++) {
+				Segment& sg = v[k];
+				uint64_t seqSize = 0;
+				for (int h = 0; h < ploidy; h++) seqSize += haps[k][h].size();
+				const uint32_t segsize = (uint32_t)((unsigned int)seqSize / (unsigned int)sg.CN);   // Segment.cpp:712-714
+				ssc_segment ss;
+				ss.first_bin = (int64_t)bins.size(); ss.n_bins = (int64_t)sg.bins.size();
+				ss.name_offset = nameOff; ss.name_len = (int32_t)nm.size();
+				const int32_t segId = (int32_t)segments.size();
+				for (auto& b : sg.bins) {
+					ssc_bin sb;
+					memset(&sb, 0, sizeof(sb));
+					const bool present = b.hap >= 0 && b.hap < ploidy && base[k][b.hap] >= 0;
+					sb.hap_base = present ? base[k][b.hap] : 0;
+					sb.contig_end = present ? contigEnd[b.hap] : 0;
+					sb.spos = (int32_t)b.spos; sb.epos = (int32_t)b.epos;
+					sb.segsize = segsize;
+					sb.read_count = (present && sg.readCount != 0) ? b.rc : 0;   // Segment::yieldReads early return, Segment.cpp:675-677
+					sb.segment = segId;
+					bins.push_back(sb);
+				}
+				segments.push_back(ss);
+				if (pw.fp) {
+					std::string r;
+					PlanWriter::app<int32_t>(r, sg.idx); PlanWriter::app<int32_t>(r, sg.CN);
+					PlanWriter::app<int64_t>(r, sg.start); PlanWriter::app<int64_t>(r, sg.end);
+					PlanWriter::app<int64_t>(r, (int64_t)segsize); PlanWriter::app<int64_t>(r, sg.readCount);
+					PlanWriter::app<int32_t>(r, (int32_t)sg.bins.size()); PlanWriter::app<int32_t>(r, ploidy);
+					for (int h = 0; h < ploidy; h++) PlanWriter::app<int64_t>(r, (int64_t)haps[k][h].size());
+					for (int h = 0; h < ploidy; h++) r += haps[k][h];
+					for (auto& b : sg.bins) PlanWriter::app<int64_t>(r, b.spos);
+					for (auto& b : sg.bins) PlanWriter::app<int64_t>(r, b.epos);
+					for (auto& b : sg.bins) PlanWriter::app<int32_t>(r, b.hap);
+					for (auto& b : sg.bins) PlanWriter::app<int32_t>(r, b.rc);
+					pw.rec(3, r);
+				}
+			}
+		}
+	}
+	if (pw.fp) { pw.rec(9, std::string()); fclose(pw.fp); }
+	if (!dev) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
+	return ssc_set_plan(dev, seed, bins.data(), (int64_t)bins.size(), segments.data(), (int64_t)segments.size(),
+	                    names.data(), (int64_t)names.size(), planned, emitted);
+}
+
+}  // namespace sschost
