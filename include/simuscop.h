@@ -167,6 +167,14 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi,
                         uint64_t* bytes1, uint64_t* bytes2, uint64_t* bases, double* device_ms);
 
+/* Host-only diagnostic (no GPU needed): the symbol the integer-threshold table built from
+ * `cdf` selects for the 32-bit draw u.  Must equal the reference's
+ * randIndx(cdf, n) with r = 2.2204e-16 + (1 - 2.2204e-16) * (u / 2^32) for every u
+ * (lib/mydefine/MyDefine.cpp:176-184); tests sweep the table boundaries with it. */
+int ssc_table_lookup_host(const double* cdf, int n, uint32_t u);
+/* Same for a 4-symbol substitution row encoded as {S0,S1,S2,base}. */
+int ssc_sub_lookup_host(const double* cdf4, uint32_t u);
+
 int ssc_get_stats(ssc_handle* h, ssc_stats* out);
 int ssc_reset_stats(ssc_handle* h);
 

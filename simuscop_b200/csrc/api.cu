@@ -641,6 +641,20 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_
 	return SSC_OK;
 }
 
+int ssc_table_lookup_host(const double* cdf, int n, uint32_t u) {
+	if (!cdf || n < 1) return -1;
+	ssc::CompressedCdf c = ssc::compress_cdf(cdf, n);
+	size_t k = 0;
+	while (k + 1 < c.T.size() && c.T[k] < u) k++;
+	return (int)c.sym[k];
+}
+
+int ssc_sub_lookup_host(const double* cdf4, uint32_t u) {
+	if (!cdf4) return -1;
+	ssc::SubRow r = ssc::make_sub_row(cdf4);
+	return (int)(r.base + (u > r.s0) + (u > r.s1) + (u > r.s2));
+}
+
 int ssc_get_stats(ssc_handle* h, ssc_stats* out) {
 	if (!h || !out) return fail(SSC_ERR_INVALID, "null argument");
 	*out = h->stats;

@@ -26,6 +26,8 @@ SCENARIOS = {
                      insertSize=250, tumor=True),
 }
 
+SCENARIOS["se_mini"] = dict(lengths=[30000], profile="GAIIx", layout="SE", coverage=2, insertSize=250, n_runs=1)
+
 VARIATION_SMALL = """\
 i\ttest\tchr20\t450010\ttcgagtcg\thomo
 i\ttest\tchr20\t1100010\ttcgagtc\thomo

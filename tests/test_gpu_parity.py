@@ -73,3 +73,27 @@ def test_batching_and_ranges_are_seamless(built, workdir):
         assert (p1, p2) == (whole1, whole2)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("name", ["pe_xten", "pe_variants", "pe_wes", "se_tumor", "pe_tiny"])
+def test_cli_end_to_end_matches_instrumented_reference(name, built, workdir):
+    """The drop-in `simuReads <config>` (C++ front end -> C ABI -> CUDA) writes the same FASTQ files."""
+    import glob
+    import os
+    import subprocess
+    from simuscop_b200 import paths, synth
+    scn = helpers.build_scenario(name, workdir)
+    plans, out_ref = helpers.run_reference_philox(scn, tag="e2e")
+    d = scn["dir"]
+    out_ours = os.path.join(d, "out_cli")
+    cfg = os.path.join(d, "cfg_cli.txt")
+    synth.write_config(cfg, output=out_ours, **scn["kw"])
+    env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_BATCH_PAIRS="4096")
+    r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref_files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(out_ref, "*.fq")))
+    our_files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(out_ours, "*.fq")))
+    assert ref_files == our_files and ref_files
+    for f in ref_files:
+        a, b = helpers.read_file(os.path.join(out_ref, f)), helpers.read_file(os.path.join(out_ours, f))
+        assert helpers.first_diff(a, b) == -1, "%s differs at byte %d" % (f, helpers.first_diff(a, b))

@@ -1,0 +1,171 @@
+"""Host-side logic on CPU: C-ABI symbols, exact threshold tables, plan parity of the C++ front end,
+pair-ID sharding (gloo, world size 2)."""
+import ctypes as C
+import glob
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from simuscop_b200 import cuda_binding, oracle_binding, paths, planfile, sharding, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _declared(header):
+    import re
+    txt = open(os.path.join(paths.ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b(ss[ch]_[a-z0-9_]+)\s*\(", txt)) - {"ssc_sink_fn"})
+
+
+def test_cuda_library_exports_every_declared_symbol(built):
+    L = C.CDLL(paths.LIB_CUDA)
+    names = _declared("simuscop.h")
+    assert "ssc_generate" in names and len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(cuda_binding.SYMBOLS) == names
+
+
+def test_host_library_exports_every_declared_symbol(built):
+    L = C.CDLL(paths.LIB_HOST)
+    for n in _declared("simuscop_host.h"):
+        assert hasattr(L, n), n
+
+
+def test_no_gpu_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cuda_binding.SscError) as e:
+        cuda_binding.Generator(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_threshold_tables_reproduce_randindx_at_every_boundary(built, tmp_path):
+    """u32 thresholds == FP64 randIndx for draws at and around every table boundary, on real profile rows."""
+    import gzip
+    p = str(tmp_path / "p.plan")
+    with gzip.open(os.path.join(GOLD, "pe_tiny.plan.gz"), "rb") as f, open(p, "wb") as g:
+        g.write(f.read())
+    plan = planfile.read_plan(p)
+    L = cuda_binding.lib()
+    O = oracle_binding.lib()
+    rng = np.random.default_rng(5)
+    t = plan.tables
+    Q = plan.hdr["n_qual"]
+    rows = [t["ins_cdf"], t["del_cdf"], t["isize_cdf"]]
+    qual = t["quality_cdf"].reshape(-1, Q)
+    rows += [qual[i] for i in rng.integers(0, qual.shape[0], 12)]
+    rows += [np.zeros(5), np.array([0.0, 0.0, 1.0, 1.0]), np.array([1e-17, 0.5, 0.5, 0.9]), np.array([0.3, 0.2, 0.9, 0.8])]
+    for cdf in rows:
+        cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+        us = {0, 1, 2, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000}
+        for c in np.unique(cdf):
+            # u such that r(u) is closest to c, and its neighbours
+            u0 = int(min(max((float(c) - 2.2204e-16) / (1 - 2.2204e-16) * 4294967296.0, 0), 4294967295))
+            us.update(max(0, min(0xFFFFFFFF, u0 + d)) for d in range(-3, 4))
+        us.update(int(x) for x in rng.integers(0, 1 << 32, 200, dtype=np.uint64))
+        for u in us:
+            assert L.ssc_table_lookup_host(cdf.ctypes.data, cdf.size, u) == O.ssco_rand_indx(cdf.ctypes.data, cdf.size, u), (u, cdf[:6])
+    sub = t["subs_cdf1"].reshape(-1, 4)
+    for i in list(rng.integers(0, sub.shape[0], 40)) + [0, sub.shape[0] - 1]:
+        cdf = np.ascontiguousarray(sub[i])
+        us = {0, 1, 0xFFFFFFFF, 0xFFFFFFFE}
+        for c in cdf:
+            u0 = int(min(max((float(c) - 2.2204e-16) / (1 - 2.2204e-16) * 4294967296.0, 0), 4294967295))
+            us.update(max(0, min(0xFFFFFFFF, u0 + d)) for d in range(-2, 3))
+        us.update(int(x) for x in rng.integers(0, 1 << 32, 50, dtype=np.uint64))
+        for u in us:
+            assert L.ssc_sub_lookup_host(cdf.ctypes.data, u) == O.ssco_rand_indx(cdf.ctypes.data, 4, u)
+
+
+def _plan_only(scn, tag):
+    d = scn["dir"]
+    cfg = os.path.join(d, "cfg_%s.txt" % tag)
+    synth.write_config(cfg, output=os.path.join(d, "out_" + tag), **scn["kw"])
+    for f in glob.glob(os.path.join(d, "plan_%s.*" % tag)):
+        os.remove(f)
+    env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_DUMP_PLAN=os.path.join(d, "plan_" + tag),
+               SIMUSCOP_PLAN_ONLY="1")
+    r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return sorted(glob.glob(os.path.join(d, "plan_%s.*.plan" % tag)), key=lambda p: int(p.split(".")[-2]))
+
+
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor"])
+def test_host_plan_matches_golden_hashes(name, built, workdir):
+    """Tables, haplotypes (SNP/SNV/indel/CNV), bins and read counts of the C++ front end, byte for byte."""
+    scn = helpers.build_scenario(name, workdir)
+    ours = _plan_only(scn, "ours")
+    gold = json.load(open(os.path.join(GOLD, "golden.json")))[name]
+    assert len(ours) == len(gold["samples"])
+    for pf, s in zip(ours, gold["samples"]):
+        assert hashlib.sha256(open(pf, "rb").read()).hexdigest() == s["plan_sha256"]
+
+
+def test_cli_argument_and_config_errors(built, tmp_path):
+    r = subprocess.run([paths.SIMUREADS], capture_output=True, text=True)
+    assert r.returncode == 1 and "configuration file is required" in r.stderr
+    r = subprocess.run([paths.SIMUREADS, "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "too many input arguments" in r.stderr
+    cfg = tmp_path / "c.txt"
+    cfg.write_text("ref = x.fa\nprofile = p\nname = t\noutput = o\ncoverage = 1\nbogus = 1\n")
+    r = subprocess.run([paths.SIMUREADS, str(cfg)], capture_output=True, text=True)
+    assert r.returncode == 1 and 'unrecognized item "bogus"' in r.stderr
+    cfg.write_text("ref = x.fa\nname = t\noutput = o\ncoverage = 1\n")
+    r = subprocess.run([paths.SIMUREADS, str(cfg)], capture_output=True, text=True)
+    assert r.returncode == 1 and "sequencing profile must be specified" in r.stderr
+
+
+def test_shard_ranges_partition():
+    for planned in (0, 1, 7, 1000, 298013245):
+        for world in (1, 2, 3, 8):
+            rs = [sharding.shard_range(planned, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == planned
+            assert all(a[1] == b[0] for a, b in zip(rs[:-1], rs[1:]))
+            assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+_WORKER = r"""
+import os, sys, gzip
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist
+from simuscop_b200 import oracle_binding, planfile, sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+plan = planfile.read_plan(sys.argv[2])
+lo, hi = sharding.shard_range(plan.planned_pairs(), rank, world)
+f1, f2, info = oracle_binding.generate(plan, 7, lo, hi)
+out = [None] * world
+dist.all_gather_object(out, (lo, hi, f1, f2))
+if rank == 0:
+    w1, w2, _ = oracle_binding.generate(plan, 7)
+    out.sort()
+    assert b"".join(o[2] for o in out) == w1 and b"".join(o[3] for o in out) == w2
+    open(sys.argv[3], "w").write("ok %d" % world)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_concatenates_to_single_rank_output(built, tmp_path):
+    """world_size 2 over gloo: each rank generates its pair-ID range (with the CPU checker standing in for a
+    GPU); the shards in rank order are byte-identical to the unsharded output."""
+    import gzip
+    p = str(tmp_path / "p.plan")
+    with gzip.open(os.path.join(GOLD, "pe_tiny.plan.gz"), "rb") as f, open(p, "wb") as g:
+        g.write(f.read())
+    w = tmp_path / "worker.py"
+    w.write_text(_WORKER)
+    flag = str(tmp_path / "ok.txt")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(w), paths.ROOT, p, flag],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(flag).read() == "ok 2"

@@ -1,0 +1,77 @@
+"""The C oracle pinned against (a) committed golden fixtures made by the instrumented reference
+(tests/golden/make_golden.py) and (b) the instrumented reference run live when its binary exists."""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from simuscop_b200 import oracle_binding, planfile
+from simuscop_b200.paths import REF_PHILOX
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gunzip(path, dst):
+    with gzip.open(path, "rb") as f, open(dst, "wb") as g:
+        g.write(f.read())
+    return dst
+
+
+def test_philox_known_answers(built):
+    # Random123 kat_vectors, philox4x32-10
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kat:
+        assert [int(x) for x in oracle_binding.philox(ctr, key)] == want
+
+
+@pytest.mark.parametrize("name", ["pe_tiny", "se_mini"])
+def test_oracle_matches_golden_fixture(name, built, tmp_path):
+    gold = json.load(open(os.path.join(GOLD, "golden.json")))[name]
+    plan = planfile.read_plan(_gunzip(os.path.join(GOLD, name + ".plan.gz"), str(tmp_path / "p.plan")))
+    f1, f2, info = oracle_binding.generate(plan, gold["seed"])
+    want1 = gzip.open(os.path.join(GOLD, name + "_1.fq.gz"), "rb").read()
+    assert f1 == want1
+    if plan.paired:
+        assert f2 == gzip.open(os.path.join(GOLD, name + "_2.fq.gz"), "rb").read()
+    s = gold["samples"][0]
+    assert hashlib.sha256(f1).hexdigest() == s["fq1_sha256"]
+    assert plan.planned_pairs() == s["planned_pairs"]
+    # abandon rule exercised: fewer pairs emitted than planned in the tiny scenario
+    if name == "pe_tiny":
+        assert info["emitted"] < plan.planned_pairs()
+
+
+def test_oracle_pair_ranges_concatenate(built, tmp_path):
+    plan = planfile.read_plan(_gunzip(os.path.join(GOLD, "pe_tiny.plan.gz"), str(tmp_path / "p.plan")))
+    whole1, whole2, _ = oracle_binding.generate(plan, 7)
+    n = plan.planned_pairs()
+    cuts = [0, 1, n // 2, n - 3, n]
+    parts = [oracle_binding.generate(plan, 7, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert b"".join(p[0] for p in parts) == whole1
+    assert b"".join(p[1] for p in parts) == whole2
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_wes"])
+def test_oracle_matches_live_instrumented_reference(name, built, workdir):
+    scn = helpers.build_scenario(name, workdir)
+    plans, out = helpers.run_reference_philox(scn, tag="pin")
+    gold = json.load(open(os.path.join(GOLD, "golden.json")))[name]
+    for i, pf in enumerate(plans):
+        plan = planfile.read_plan(pf)
+        r1p, r2p = helpers.sample_files(out, plan, i, scn)
+        r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
+        f1, f2, _ = oracle_binding.generate(plan, scn["seed"])
+        assert f1 == r1 and f2 == r2
+        # and the live run reproduces the committed hashes (the instrumented build is deterministic)
+        assert hashlib.sha256(r1).hexdigest() == gold["samples"][i]["fq1_sha256"]
+        assert hashlib.sha256(open(pf, "rb").read()).hexdigest() == gold["samples"][i]["plan_sha256"]
