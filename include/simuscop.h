@@ -118,6 +118,9 @@ typedef struct ssc_stats {
 	uint64_t hap_bytes;        /* algorithmic haplotype bytes read: ceil(len/4)+ceil(len/8) per fragment */
 	uint64_t d2h_bytes;
 	uint64_t h2d_bytes;
+	double   gen_kernel_ms;    /* CUDA-event time of the generation kernel alone (ssc_generate_device) */
+	double   compact_kernel_ms;/* CUDA-event time of the compaction kernel alone (ssc_generate_device) */
+	uint64_t timed_batches;    /* launches covered by gen_kernel_ms */
 } ssc_stats;
 
 /*

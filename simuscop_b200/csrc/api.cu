@@ -111,6 +111,10 @@ struct ssc_handle {
 	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
 	ssc::BatchResult* h_result[2] = {nullptr, nullptr};
 
+	std::vector<cudaEvent_t> kev;   // per-batch kernel timing events of ssc_generate_device (3 per batch)
+	int kevUsed = 0;
+	bool timeKernels = false;
+
 	ssc_stats stats;
 };
 
@@ -197,7 +201,13 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
 		P.slotLens = h->d_slotLens.p;
-		CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s));
+		cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+		if (h->timeKernels) {
+			while ((int)h->kev.size() < h->kevUsed + 3) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }
+			e0 = h->kev[h->kevUsed]; e1 = h->kev[h->kevUsed + 1]; e2 = h->kev[h->kevUsed + 2];
+			h->kevUsed += 3;
+		}
+		CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, e2));
 		h->stats.launches += 1;
 	} else {
 		ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
@@ -287,6 +297,7 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_hap2.release(); h->d_hapN.release();
 	h->d_slotLens.release(); h->d_ticket2.release();
 	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
+	for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
 	if (h->evStart) cudaEventDestroy(h->evStart);
 	if (h->evStop) cudaEventDestroy(h->evStop);
 	if (h->compute) cudaStreamDestroy(h->compute);
@@ -608,6 +619,7 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_
 	uint64_t b1 = 0, b2 = 0, nb = 0;
 	float ms = 0;
 	if (eHi > eLo) {
+		h->timeKernels = true; h->kevUsed = 0;
 		CK(cudaEventRecord(h->evStart, h->compute));
 		int k = 0;
 		for (int64_t e = eLo; e < eHi; e += h->slabPairs, k++) {
@@ -633,6 +645,13 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_
 		}
 		CK(cudaEventElapsedTime(&ms, h->evStart, h->evStop));
 		h->stats.device_ms += ms;
+		h->timeKernels = false;
+		for (int i = 0; i + 2 < h->kevUsed; i += 3) {
+			float a = 0, b = 0;
+			CK(cudaEventElapsedTime(&a, h->kev[i], h->kev[i + 1]));
+			CK(cudaEventElapsedTime(&b, h->kev[i + 1], h->kev[i + 2]));
+			h->stats.gen_kernel_ms += a; h->stats.compact_kernel_ms += b; h->stats.timed_batches += 1;
+		}
 	}
 	if (bytes1) *bytes1 = b1;
 	if (bytes2) *bytes2 = b2;

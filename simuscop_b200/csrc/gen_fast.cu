@@ -698,9 +698,11 @@ static cudaError_t launch_fast_variant(const GenParams& P, size_t smemBytes, int
 }
 
 // P.out1/out2 = slot scratch, P.dense1/dense2 = final slabs, P.nTiles = groups of FG_WORKERS pairs
-cudaError_t launch_generate_fast(const GenParams& P, bool qsmem, size_t smemBytes, int grid, int smCount, cudaStream_t stream) {
+cudaError_t launch_generate_fast(const GenParams& P, bool qsmem, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
+                                 cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
 	const int nch = (P.t.RL + 31) / 32;
 	cudaError_t e;
+	if (e0) cudaEventRecord(e0, stream);
 	if (qsmem) {
 		if (nch <= 3) e = launch_fast_variant<3, 8>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 8>(P, smemBytes, grid, stream);
@@ -711,11 +713,13 @@ cudaError_t launch_generate_fast(const GenParams& P, bool qsmem, size_t smemByte
 		else e = launch_fast_variant<5, 0>(P, smemBytes, grid, stream);
 	}
 	if (e != cudaSuccess) return e;
+	if (e1) cudaEventRecord(e1, stream);
 	const int nSlots = (int)(P.emitHi - P.emitLo);
 	const int nTiles = (nSlots + CP_THREADS - 1) / CP_THREADS;
 	int cgrid = smCount * 8;
 	if (cgrid > nTiles) cgrid = nTiles;
 	compact_kernel<<<cgrid, CP_THREADS, 0, stream>>>(P, nSlots, nTiles);
+	if (e2) cudaEventRecord(e2, stream);
 	return cudaGetLastError();
 }
 
