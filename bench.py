@@ -58,7 +58,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -247,19 +247,21 @@ def main():
     planned, emitted = job.prepare(0, gen)
     t_plan = time.perf_counter() - t0
     lo, hi = sharding.shard_range(planned, rank, world)
-    need = (a.warmup + a.steps) * a.batch_pairs
-    if hi - lo < 2 * need:
-        raise SystemExit("shard of %d pairs is too small for %d steps of %d pairs (device + e2e legs)" % (hi - lo, a.warmup + a.steps, a.batch_pairs))
+    nbatch = (hi - lo) // a.batch_pairs
+    if nbatch < 4:
+        raise SystemExit("shard of %d pairs is too small for batches of %d pairs" % (hi - lo, a.batch_pairs))
 
     def step_range(k):
-        s = lo + k * a.batch_pairs
+        # consecutive batches of this rank's shard, wrapping around (a batch is revisited only after >= 3 others,
+        # i.e. after several GB of other traffic: nothing of it is left in the 126 MB L2)
+        s = lo + (k % nbatch) * a.batch_pairs
         return s, s + a.batch_pairs
 
     # ---------------- device-resident leg: outputs stay in HBM
+    sampler = ClockSampler(local) if rank == 0 else None
     for k in range(a.warmup):
         gen.generate_device(*step_range(k))
     gen.reset_stats()
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
     bases = 0
@@ -269,7 +271,6 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     barrier()
-    clocks = sampler.stop() if sampler else None
     st = gen.stats()
     dev_ms = st["device_ms"]
 
@@ -292,6 +293,7 @@ def main():
     dt_e2e = time.perf_counter() - t1
     barrier()
     st2 = gen.stats()
+    clocks = sampler.stop() if sampler else None
 
     def allmax(x):
         if world == 1:
