@@ -116,6 +116,8 @@ public:
 
 	// Streams sample `s` into the device handle: haplotype store + plan.  dumpPath (optional): SSCPLAN1 file.
 	int prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int64_t* planned, int64_t* emitted);
+	// same, replicated into several device handles (one per GPU); an empty list = plan-only mode
+	int prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const std::string& dumpPath, int64_t* planned, int64_t* emitted);
 private:
 	void load_variations();
 	void load_snps();

@@ -5,7 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/simuscop_host.h"
 #include "host.h"
@@ -61,7 +65,6 @@ int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_pa
 }
 
 int ssh_run(ssh_job* job, int device) {
-	ssc_handle* dev = nullptr;
 	if (getenv("SIMUSCOP_PLAN_ONLY")) {
 		// host logic only (no GPU): write the SSCPLAN1 dumps of every sample and stop
 		const char* prefix = getenv("SIMUSCOP_DUMP_PLAN");
@@ -73,34 +76,77 @@ int ssh_run(ssh_job* job, int device) {
 		}
 		return 0;
 	}
-	int rc = ssc_create(device, &dev);
-	if (rc) { std::cerr << "Error: " << ssc_last_error() << std::endl; return rc; }
+	// devices: SIMUSCOP_DEVICES="0,1,2,..." shards every sample by pair-ID range over the listed GPUs
+	std::vector<int> devIds;
+	if (const char* dl = getenv("SIMUSCOP_DEVICES")) {
+		for (const std::string& t : sschost::split(dl, ',')) if (!sschost::trim(t).empty()) devIds.push_back(atoi(t.c_str()));
+	}
+	if (devIds.empty()) devIds.push_back(device);
+	std::vector<ssc_handle*> devs;
+	int rc = 0;
+	for (int id : devIds) {
+		ssc_handle* h = nullptr;
+		rc = ssc_create(id, &h);
+		if (rc) { std::cerr << "Error: " << ssc_last_error() << std::endl; for (auto* d : devs) ssc_destroy(d); return rc; }
+		devs.push_back(h);
+	}
 	const char* dumpPrefix = getenv("SIMUSCOP_DUMP_PLAN");
-	const char* bp = getenv("SIMUSCOP_BATCH_PAIRS");
-	if (bp) ssc_set_option(dev, "batch_pairs", atoll(bp));
+	if (const char* bp = getenv("SIMUSCOP_BATCH_PAIRS")) for (auto* d : devs) ssc_set_option(d, "batch_pairs", atoll(bp));
 	sschost::Job& J = job->job;
-	for (int s = 0; s < (int)J.samples.size(); s++) {
+	const int G = (int)devs.size();
+	for (int s = 0; s < (int)J.samples.size() && !rc; s++) {
 		const std::string prefix = J.cfg.str["output"] + "/" + J.samples[s].stem;
-		FileSink sink;
 		const bool paired = J.cfg.paired();
 		const std::string f1 = paired ? prefix + "_1.fq" : prefix + ".fq";
-		sink.fd1 = open(f1.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-		if (sink.fd1 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + f1);
-		if (paired) {
-			const std::string f2 = prefix + "_2.fq";
-			sink.fd2 = open(f2.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-			if (sink.fd2 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + f2);
-		}
+		const std::string f2 = paired ? prefix + "_2.fq" : "";
 		std::string dump;
 		if (dumpPrefix) dump = std::string(dumpPrefix) + "." + std::to_string(s) + ".plan";
 		int64_t planned = 0, emitted = 0;
-		rc = J.prepare_sample(s, dev, dump, &planned, &emitted);
-		if (!rc) rc = ssc_generate(dev, 0, planned, file_sink, &sink);
-		close(sink.fd1);
-		if (sink.fd2 >= 0) close(sink.fd2);
+		rc = J.prepare_sample_multi(s, devs, dump, &planned, &emitted);
 		if (rc) { std::cerr << "Error: " << ssc_last_error() << std::endl; break; }
+		// shard g writes <file>.part<g> (g > 0) or the final file (g == 0); parts are appended in rank order afterwards
+		std::vector<FileSink> sinks(G);
+		std::vector<int> rcs(G, 0);
+		std::vector<std::string> errs(G);
+		auto part = [&](const std::string& f, int g) { return g == 0 ? f : f + ".part" + std::to_string(g); };
+		for (int g = 0; g < G; g++) {
+			sinks[g].fd1 = open(part(f1, g).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+			if (sinks[g].fd1 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + part(f1, g));
+			if (paired) {
+				sinks[g].fd2 = open(part(f2, g).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+				if (sinks[g].fd2 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + part(f2, g));
+			}
+		}
+		auto work = [&](int g) {
+			const int64_t base = planned / G, extra = planned % G;
+			const int64_t lo = g * base + std::min<int64_t>(g, extra), hi = lo + base + (g < extra ? 1 : 0);
+			rcs[g] = ssc_generate(devs[g], lo, hi, file_sink, &sinks[g]);
+			if (rcs[g]) errs[g] = ssc_last_error();
+		};
+		std::vector<std::thread> th;
+		for (int g = 1; g < G; g++) th.emplace_back(work, g);
+		work(0);
+		for (auto& t : th) t.join();
+		for (int g = 0; g < G; g++) if (rcs[g]) { std::cerr << "Error: " << errs[g] << std::endl; rc = rcs[g]; }
+		// ordered concatenation of the shards
+		for (int g = 1; g < G && !rc; g++) {
+			for (int f = 0; f < (paired ? 2 : 1); f++) {
+				const int src = f == 0 ? sinks[g].fd1 : sinks[g].fd2;
+				const int dst = f == 0 ? sinks[0].fd1 : sinks[0].fd2;
+				close(src);
+				const std::string pf = part(f == 0 ? f1 : f2, g);
+				int in = open(pf.c_str(), O_RDONLY);
+				std::vector<char> buf(8u << 20);
+				ssize_t n;
+				while (in >= 0 && (n = read(in, buf.data(), buf.size())) > 0) if (write_all(dst, buf.data(), (size_t)n)) { rc = SSC_ERR_SINK; break; }
+				if (in >= 0) close(in);
+				unlink(pf.c_str());
+			}
+		}
+		close(sinks[0].fd1);
+		if (sinks[0].fd2 >= 0) close(sinks[0].fd2);
 	}
-	ssc_destroy(dev);
+	for (auto* d : devs) ssc_destroy(d);
 	return rc;
 }
 

@@ -322,6 +322,12 @@ struct PlanWriter {
 }  // namespace
 
 int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int64_t* planned, int64_t* emitted) {
+	std::vector<ssc_handle*> devs;
+	if (dev) devs.push_back(dev);
+	return prepare_sample_multi(s, devs, dumpPath, planned, emitted);
+}
+
+int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const std::string& dumpPath, int64_t* planned, int64_t* emitted) {
 	begin_plan();
 	const Sample& sm = samples[s];
 	const int ploidy = cfg.num["ploidy"];
@@ -329,8 +335,8 @@ int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int
 	// dev == nullptr: plan-only mode (no GPU needed): store offsets are tracked locally, the plan is only dumped
 	ssc_profile_tables pt;
 	prof.fill(&pt, cfg);
-	int rc = dev ? ssc_set_profile(dev, &pt) : 0;
-	if (rc) return rc;
+	int rc = 0;
+	for (ssc_handle* dev : devs) { rc = ssc_set_profile(dev, &pt); if (rc) return rc; }
 	uint64_t localSize = 0;
 
 	// populations of this sample and their read budgets (Genome.cpp:868, 931-936)
@@ -370,8 +376,7 @@ int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int
 			for (auto& in : inss[pp.first][chr]) insTotal += in.seq.length();
 			for (auto& sg : segs[pp.first][chr]) reserve += (uint64_t)std::max(sg.CN, 1) * ((uint64_t)sg.refSize() + insTotal);
 		}
-	rc = dev ? ssc_genome_reserve(dev, reserve + 1024) : 0;
-	if (rc) return rc;
+	for (ssc_handle* dev : devs) { rc = ssc_genome_reserve(dev, reserve + 1024); if (rc) return rc; }
 
 	std::vector<ssc_bin> bins;
 	std::vector<ssc_segment> segments;
@@ -400,8 +405,7 @@ int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int
 				for (size_t k = 0; k < v.size(); k++) {
 					if (haps[k][h].empty()) continue;
 					uint64_t first = localSize;
-					rc = dev ? ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first) : 0;
-					if (rc) return rc;
+					for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
 					base[k][h] = (int64_t)first;
 					localSize = first + haps[k][h].size();
 				}
@@ -447,9 +451,13 @@ int Job::prepare_sample(int s, ssc_handle* dev, const std::string& dumpPath, int
 		}
 	}
 	if (pw.fp) { pw.rec(9, std::string()); fclose(pw.fp); }
-	if (!dev) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
-	return ssc_set_plan(dev, seed, bins.data(), (int64_t)bins.size(), segments.data(), (int64_t)segments.size(),
-	                    names.data(), (int64_t)names.size(), planned, emitted);
+	if (devs.empty()) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
+	for (ssc_handle* dev : devs) {
+		rc = ssc_set_plan(dev, seed, bins.data(), (int64_t)bins.size(), segments.data(), (int64_t)segments.size(),
+		                  names.data(), (int64_t)names.size(), planned, emitted);
+		if (rc) return rc;
+	}
+	return 0;
 }
 
 }  // namespace sschost

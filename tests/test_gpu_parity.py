@@ -97,3 +97,26 @@ def test_cli_end_to_end_matches_instrumented_reference(name, built, workdir):
     for f in ref_files:
         a, b = helpers.read_file(os.path.join(out_ref, f)), helpers.read_file(os.path.join(out_ours, f))
         assert helpers.first_diff(a, b) == -1, "%s differs at byte %d" % (f, helpers.first_diff(a, b))
+
+
+def test_cli_sharded_over_two_handles_is_byte_identical(built, workdir):
+    """SIMUSCOP_DEVICES shards every sample by pair-ID range (one host thread + one handle per entry); the ordered
+    concatenation equals the single-handle output.  "0,0" exercises the path on a single-GPU box."""
+    import os
+    import subprocess
+    import torch
+    from simuscop_b200 import paths, synth
+    scn = helpers.build_scenario("pe_variants", workdir)
+    d = scn["dir"]
+    outs = {}
+    devs = "0,1,0" if torch.cuda.device_count() >= 2 else "0,0,0"
+    for tag, env_extra in (("one", {}), ("three", {"SIMUSCOP_DEVICES": devs})):
+        out = os.path.join(d, "out_sh_" + tag)
+        cfg = os.path.join(d, "cfg_sh_%s.txt" % tag)
+        synth.write_config(cfg, output=out, **scn["kw"])
+        env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_BATCH_PAIRS="8192", **env_extra)
+        r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[tag] = (helpers.read_file(os.path.join(out, "test_1.fq")), helpers.read_file(os.path.join(out, "test_2.fq")))
+        assert sorted(os.listdir(out)) == ["test_1.fq", "test_2.fq"]
+    assert outs["one"] == outs["three"] and len(outs["one"][0]) > 0
