@@ -78,6 +78,15 @@ __device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t& lo, ui
 	asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 
+// acc += (a > b) for unsigned a, b: one ISETP + one predicated IADD
+__device__ __forceinline__ void add_gt(uint32_t& acc, uint32_t a, uint32_t b) {
+	asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(acc) : "r"(a), "r"(b));
+}
+// acc += inc if a < b (unsigned)
+__device__ __forceinline__ void add_lt(uint32_t& acc, uint32_t a, uint32_t b, uint32_t inc) {
+	asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(acc) : "r"(a), "r"(b), "r"(inc));
+}
+
 // Philox4x32-10 with the counter layout of philox.cuh::draw_block
 __device__ __forceinline__ u32x4 philox_fast(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -173,6 +182,9 @@ struct WarpCtx {
 };
 
 // substitution + quality for one output base; returns (char | qual << 8)
+template <int QP> __device__ __forceinline__ uint32_t qual_lookup(const uint32_t* qualT, const uint8_t* qualSym, int pitch, int qrow, uint32_t u3);
+
+template <int QP>
 __device__ __forceinline__ uint32_t call_base(const WarpCtx& w, uint32_t cur, int row, bool bad, bool curN, int binIdx,
                                               uint32_t u2, uint32_t u3) {
 	int call;
@@ -186,10 +198,7 @@ __device__ __forceinline__ uint32_t call_base(const WarpCtx& w, uint32_t cur, in
 	else {
 		ch = __byte_perm(w.baseChars, 0, 0x4440 | call);
 		const int qrow = ((int)cur * 4 + call) * w.B + binIdx;
-		const uint32_t* qt = w.qualT + qrow * w.qualPitch;
-		int k = 0;
-		for (int s = w.qualPitch >> 1; s > 0; s >>= 1) if (qt[k + s - 1] < u3) k += s;
-		q = w.qualSym[qrow * w.qualPitch + k];
+		q = qual_lookup<QP>(w.qualT, w.qualSym, w.qualPitch, qrow, u3);
 	}
 	return ch | (q << 8);
 }
@@ -209,6 +218,7 @@ __device__ __forceinline__ uint32_t window_code(const WarpCtx& w, int relBase /*
 // Slow path of Profile::predict (a read with at least one indel candidate): compact, not unrolled.
 // evbits: per lane, bit 2c = insertion test hit at cycle 32c+lane, bit 2c+1 = deletion test hit.
 // Writes bases/quals into stage[H ..]; returns m.
+template <int QP>
 __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int mate, bool rev, int relFirst,
                                       uint8_t* stage, int H, unsigned int* errorFlags, const uint32_t* xsave, int nSaved) {
 	const int RL = w.RL, lane = w.lane;
@@ -299,7 +309,7 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 			const int row = j >= 2 ? (int)(20u + 16u * (p2 & 3u) + 4u * (p1 & 3u) + (cur & 3u))
 			                       : j == 1 ? (int)(4u + 4u * (p1 & 3u) + (cur & 3u)) : (int)(cur & 3u);
 			const int binIdx = (int)__umulhi((uint32_t)(j * w.B), inv);
-			const uint32_t r = call_base(w, cur & 3u, row, bad, (cur & 4u) != 0, binIdx, u2, u3);
+			const uint32_t r = call_base<QP>(w, cur & 3u, row, bad, (cur & 4u) != 0, binIdx, u2, u3);
 			stage[H + j] = (uint8_t)r;
 			stage[H + m + 3 + j] = (uint8_t)(r >> 8);
 		}
@@ -313,9 +323,10 @@ template <int QP>
 __device__ __forceinline__ uint32_t qual_lookup(const uint32_t* qualT, const uint8_t* qualSym, int pitch, int qrow, uint32_t u3) {
 	if (QP == 8) {
 		const uint32_t* qt = qualT + qrow * 8;
-		int k = (qt[3] < u3) ? 4 : 0;
-		k += (qt[k + 1] < u3) ? 2 : 0;
-		k += (qt[k] < u3) ? 1 : 0;
+		uint32_t k = 0;
+		add_lt(k, qt[3], u3, 4u);
+		add_lt(k, qt[k + 1], u3, 2u);
+		add_lt(k, qt[k], u3, 1u);
 		return qualSym[qrow * 8 + k];
 	} else {
 		const uint32_t* qt = qualT + qrow * pitch;
@@ -352,7 +363,9 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 #pragma unroll 1
 	for (int i = threadIdx.x; i < nSubTotal; i += FG_THREADS) s_sub[i] = t.sub[i];
 #pragma unroll 1
-	for (int i = threadIdx.x; i < nQual; i += FG_THREADS) { s_qualT[i] = t.qualT[i]; s_qualSym[i] = t.qualSym[i]; }
+	for (int i = threadIdx.x; i < nQual / 4; i += FG_THREADS) ((uint4*)s_qualT)[i] = ((const uint4*)t.qualT)[i];
+#pragma unroll 1
+	for (int i = threadIdx.x; i < nQual / 16; i += FG_THREADS) ((uint4*)s_qualSym)[i] = ((const uint4*)t.qualSym)[i];
 #pragma unroll 1
 	for (int i = threadIdx.x; i < t.nIsize; i += FG_THREADS) { s_isizeT[i] = t.isizeT[i]; s_isizeSym[i] = t.isizeSym[i]; }
 #pragma unroll 1
@@ -442,15 +455,19 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 		}
 
 		// ---- header digits: lanes 0..9 digit d of posmod, lanes 10..19 digit d of fragCount
-		const int nd1 = f_ndigits(posmod), nd2 = f_ndigits(fragCount);
 		const uint32_t dsrc = lane < 10 ? posmod : fragCount;
 		const int dpos = lane < 10 ? lane : (lane < 20 ? lane - 10 : 0);
-		const uint32_t dg = '0' + (dsrc / c_pow10[dpos]) % 10u;
+		const uint32_t p10 = c_pow10[dpos];
+		const uint32_t geMask = __ballot_sync(0xffffffffu, dsrc >= p10);          // digit d exists iff value >= 10^d
+		const int nd1 = 1 + __popc(geMask & 0x3feu), nd2 = 1 + __popc(geMask & 0xff800u);
+		const uint32_t dg = '0' + (dsrc / p10) % 10u;
 		const int nameLen = bin.name_len;
 		const int H = nameLen + nd1 + 1 + nd2 + (t.paired ? 2 : 0) + 1;
-		uint32_t hb[3];
+		uint32_t hb[3] = {0, 0, 0};
+		const int hWords = (H + 31) >> 5;
 #pragma unroll
 		for (int r = 0; r < 3; r++) {
+			if (r >= hWords) break;
 			const int i = lane + 32 * r;
 			uint32_t ch = '\n';
 			int srcLane = 0;
@@ -501,6 +518,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 			// ---- header
 #pragma unroll
 			for (int r = 0; r < 3; r++) {
+				if (r >= hWords) break;
 				const int i = lane + 32 * r;
 				if (i < H) stage[i] = (uint8_t)((t.paired && i == H - 2) ? ('1' + mate) : hb[r]);
 			}
@@ -536,7 +554,8 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 					const uint32_t binIdx = __umulhi(c == NCH - 1 ? min(jB, (uint32_t)((RL - 1) * B)) : jB, invRL);
 					jB += 32u * (uint32_t)B;
 					const uint4 sr = subM[row * (uint32_t)B + binIdx];
-					uint32_t call = sr.w + (x2[c] > sr.x) + (x2[c] > sr.y) + (x2[c] > sr.z);
+					uint32_t call = sr.w;
+					add_gt(call, x2[c], sr.x); add_gt(call, x2[c], sr.y); add_gt(call, x2[c], sr.z);
 					call = n3 ? cur : call;                                        // unknown context: base passes through
 					const uint32_t qrow = (cur * 4u + call) * (uint32_t)B + binIdx;
 					uint32_t q = qual_lookup<QP>(qualT, qualSym, qPitch, (int)qrow, x3[c]);
@@ -552,7 +571,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 				for (int c = 0; c < NCH; c++) { s_xsave[c * 32 + lane] = x2[c]; s_xsave[160 + c * 32 + lane] = x3[c]; }
 				__syncwarp();
 				const int relFirst = rev ? (dOff + RL - 1) : dOff;
-				m = slow_read(w, evbits, mate, rev, relFirst, stage, H, &P.result->errorFlags, s_xsave, NCH * 32);
+				m = slow_read<QP>(w, evbits, mate, rev, relFirst, stage, H, &P.result->errorFlags, s_xsave, NCH * 32);
 			}
 			if (lane == 0) { stage[H + m] = '\n'; stage[H + m + 1] = '+'; stage[H + m + 2] = '\n'; stage[H + 2 * m + 3] = '\n'; }
 			lens |= (uint32_t)(H + 2 * m + 4) << (16 * mate);
