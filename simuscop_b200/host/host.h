@@ -76,6 +76,7 @@ struct Segment {
 	int idx; std::string chr; long start, end; int CN, mCN;
 	std::vector<int> seqReps, mIndx, targetIdx;
 	std::vector<Bin> bins; bool weighted = false;
+	std::vector<std::string> hapCache;   // haplotypes kept between the weights pass and materialisation (memory permitting)
 	long readCount = 0;
 	long refSize() const { return end - start + 1; }
 };
@@ -111,6 +112,8 @@ public:
 	void build_haplotypes(Segment& seg, const std::string& popu, std::vector<std::string>& haps);
 	// bins + weights (Segment::getWeightedLength, Segment.cpp:550-641)
 	double weighted_length(Segment& seg, const std::string& popu);
+	double weighted_length_from(Segment& seg, const std::vector<std::string>& haps);
+	long long hapCacheBudget = 0;                             // bytes of haplotype strings that may stay cached
 	void set_read_counts(const std::string& popu, long reads);   // Genome::setReadCounts, Genome.cpp:783-825
 	void begin_plan();                                        // reads, ACNs, srand (Genome.cpp:831-852)
 

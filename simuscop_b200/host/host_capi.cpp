@@ -71,7 +71,7 @@ int ssh_run(ssh_job* job, int device) {
 		if (!prefix) { std::cerr << "Error: SIMUSCOP_PLAN_ONLY needs SIMUSCOP_DUMP_PLAN" << std::endl; return 1; }
 		for (int s = 0; s < (int)job->job.samples.size(); s++) {
 			int64_t a, b;
-			int r = job->job.prepare_sample(s, nullptr, std::string(prefix) + "." + std::to_string(s) + ".plan", &a, &b);
+			int r = job->job.prepare_sample(s, nullptr, std::string(prefix) == "none" ? std::string() : std::string(prefix) + "." + std::to_string(s) + ".plan", &a, &b);
 			if (r) return r;
 		}
 		return 0;

@@ -1,5 +1,6 @@
 // host_io.cpp -- configuration file, FASTA/.fai, SNP / variation / target / abundance loaders.
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -185,13 +186,21 @@ const std::string& Fasta::chromosome(const std::string& chr) {
 	fseeko(f, (off_t)e.offset, SEEK_SET);
 	size_t got = fread(&buf[0], 1, raw, f);
 	fclose(f);
-	cached_.clear();
-	cached_.reserve((size_t)e.length);
-	for (size_t i = 0; i < got && cached_.size() < (size_t)e.length; i++) {
-		char c = buf[i];
-		if (c == '\n' || c == '\0') continue;
-		cached_.push_back((char)toupper((unsigned char)c));
+	cached_.assign((size_t)e.length, 'N');
+	static unsigned char up[256];
+	if (!up['a']) for (int i = 0; i < 256; i++) up[i] = (unsigned char)toupper(i);
+	size_t w = 0, i = 0;
+	while (i < got && w < (size_t)e.length) {
+		const char* nlp = (const char*)memchr(buf.data() + i, '\n', got - i);
+		size_t lineEnd = nlp ? (size_t)(nlp - buf.data()) : got;
+		size_t n = std::min(lineEnd - i, (size_t)e.length - w);
+		char* dst = &cached_[w];
+		const unsigned char* src = (const unsigned char*)buf.data() + i;
+		for (size_t k = 0; k < n; k++) dst[k] = (char)up[src[k]];
+		w += n;
+		i = lineEnd + 1;
 	}
+	cached_.resize(w);
 	cachedName_ = chr;
 	return cached_;
 }
@@ -378,6 +387,12 @@ void Job::load_abundance() {
 
 void Job::open(const std::string& configPath) {
 	cfg.load(configPath);
+	{
+		// haplotype strings may stay in host memory between the two plan passes: 40 % of RAM unless SIMUSCOP_HOST_CACHE_GB says otherwise
+		const char* e = getenv("SIMUSCOP_HOST_CACHE_GB");
+		long long phys = (long long)sysconf(_SC_PHYS_PAGES) * (long long)sysconf(_SC_PAGE_SIZE);
+		hapCacheBudget = e ? (long long)(atof(e) * 1e9) : (long long)(0.4 * (double)phys);
+	}
 	// Genome::loadData, lib/genome/Genome.cpp:17-30
 	load_variations();
 	load_snps();

@@ -74,8 +74,10 @@ void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<st
 	haps.assign(ploidy, std::string());
 	if (seg.CN == 0) die(1, "ERROR: copy number 0 segments are not supported (" + popu + " " + seg.chr + ":" + std::to_string(seg.start) + ")");
 	const std::string& chrSeq = fasta.chromosome(seg.chr);
-	std::string ref = chrSeq.substr((size_t)(seg.start - 1), (size_t)seg.refSize());
-	const unsigned int refSize = (unsigned int)ref.size();
+	const size_t refOff = (size_t)(seg.start - 1);
+	const size_t refLen = std::min((size_t)seg.refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
+	const char* ref = chrSeq.data() + refOff;
+	const unsigned int refSize = (unsigned int)refLen;
 	const int CN = seg.CN, mCN = seg.mCN;
 	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
 	if (seg.mIndx.empty()) {
@@ -110,15 +112,17 @@ void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<st
 	}
 	if (CN < ploidy) {
 		for (int i = 0; i < ploidy; i++)
-			if (std::find(seg.seqReps.begin(), seg.seqReps.end(), i) != seg.seqReps.end()) haps[i] = ref;
+			if (std::find(seg.seqReps.begin(), seg.seqReps.end(), i) != seg.seqReps.end()) haps[i].assign(ref, refLen);
 	} else {
 		for (int i = 0; i < ploidy; i++) {
 			haps[i].reserve((size_t)refSize * seg.seqReps[i] + 64);
-			for (int j = 0; j < seg.seqReps[i]; j++) haps[i] += ref;
+			for (int j = 0; j < seg.seqReps[i]; j++) haps[i].append(ref, refLen);
 		}
 	}
+	bool touched = false;   // the reference is already upper case: the final toupper only matters after a variant was applied
 	auto poke = [&](std::string& h, int sindx, char c) {
 		unsigned int len = (unsigned int)h.length();
+		touched = true;
 		for (unsigned int t = 0; t < len / refSize; t++) h[sindx + t * refSize] = c;
 	};
 	// SNPs: heterozygous, alternating between the major set and its complement (Segment.cpp:233-265)
@@ -155,6 +159,7 @@ void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<st
 			for (int j = 0; j < ploidy; j++) {
 				if (in.het && ((k == 0 && !inM(j)) || (k == 1 && inM(j)))) continue;
 				int offset = 0;
+				touched = true;
 				for (auto& kv : insMap[j]) if (kv.first <= sindx) offset += kv.second;
 				std::string& h = haps[j];
 				int n = (int)(h.length() / (refSize + insLens[j]));
@@ -185,7 +190,8 @@ void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<st
 			if (d.het) k = (k + 1) % 2;
 		}
 	}
-	for (auto& h : haps) std::transform(h.begin(), h.end(), h.begin(), [](unsigned char c) { return (char)toupper(c); });
+	if (touched)
+		for (auto& h : haps) std::transform(h.begin(), h.end(), h.begin(), [](unsigned char c) { return (char)toupper(c); });
 }
 
 // calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303
@@ -193,9 +199,9 @@ static int gc_percent(const char* s, size_t n) {
 	if (n == 0) return 0;
 	int gc = 0, nn = 0;
 	for (size_t i = 0; i < n; i++) {
-		char c = s[i];
-		if (c == 'G' || c == 'C') gc++;
-		else if (c == 'N') nn++;
+		const char c = s[i];
+		gc += (c == 'G') | (c == 'C');
+		nn += (c == 'N');
 	}
 	if (nn > 0) return -1;
 	return 100 * gc / (int)(n - nn);
@@ -208,10 +214,20 @@ double Job::weighted_length(Segment& seg, const std::string& popu) {
 		for (auto& b : seg.bins) wl += b.weight;
 		return wl;
 	}
-	const int ploidy = cfg.num["ploidy"];
-	const unsigned int fragSize = 1000;
 	std::vector<std::string> haps;
 	build_haplotypes(seg, popu, haps);
+	wl = weighted_length_from(seg, haps);
+	// keep the strings for the materialisation pass when they fit the host budget (saves the second build)
+	size_t bytes = 0;
+	for (auto& h : haps) bytes += h.size();
+	if ((long long)bytes <= hapCacheBudget) { hapCacheBudget -= (long long)bytes; seg.hapCache.swap(haps); }
+	return wl;
+}
+
+double Job::weighted_length_from(Segment& seg, const std::vector<std::string>& haps) {
+	double wl = 0;
+	const int ploidy = cfg.num["ploidy"];
+	const unsigned int fragSize = 1000;
 	if (targets.empty()) {
 		for (int i = 0; i < ploidy; i++) {
 			const std::string& p = haps[i];
@@ -391,7 +407,15 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 			names += nm;
 			// materialise the chromosome's haplotypes (Genome.cpp:876-878)
 			std::vector<std::vector<std::string>> haps(v.size());
-			for (size_t k = 0; k < v.size(); k++) build_haplotypes(v[k], popu, haps[k]);
+			for (size_t k = 0; k < v.size(); k++) {
+				if (!v[k].hapCache.empty()) {     // kept from the weights pass (same strings: generateSegSequences is deterministic once mIndx is set)
+					size_t b = 0;
+					for (auto& h : v[k].hapCache) b += h.size();
+					haps[k].swap(v[k].hapCache);
+					v[k].hapCache.clear(); v[k].hapCache.shrink_to_fit();
+					hapCacheBudget += (long long)b;
+				} else build_haplotypes(v[k], popu, haps[k]);
+			}
 			if (pw.fp) {
 				std::string u;
 				PlanWriter::app<int32_t>(u, (int32_t)popu.size()); PlanWriter::app<int32_t>(u, (int32_t)chr.size());

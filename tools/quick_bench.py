@@ -19,7 +19,7 @@ plans, out = helpers.run_reference_philox(scn)
 plan = planfile.read_plan(plans[0])
 plan.bins["read_count"] *= scale
 g = cuda_binding.Generator(0)
-g.set_option("batch_pairs", 1 << 21)
+g.set_option("batch_pairs", int(os.environ.get("QB_BATCH", 1 << 21)))
 t = time.time()
 g.load_plan(plan, 7)
 print("load_plan %.2fs planned=%d emitted=%d" % (time.time() - t, g.planned, g.emitted))
