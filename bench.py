@@ -323,6 +323,13 @@ def main():
         nb = max(1, st["timed_batches"])
         gen_ms = st["gen_kernel_ms"] / nb
         achieved = alg_bytes / nb / (gen_ms / 1000.0) / 1e9 if gen_ms > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["generate_slots_kernel"]
+            if tr["batch_pairs"] == a.batch_pairs:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": "simulated_bases_per_sec", "value": tot_bases / T, "unit": "bases/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * T / a.steps, "higher_is_better": True,
@@ -341,10 +348,13 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "generate_slots_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "generate_slots_kernel",
                          "kernel_ms_per_launch": gen_ms, "compact_kernel_ms_per_launch": st["compact_kernel_ms"] / nb,
                          "algorithmic_bytes_per_launch": alg_bytes / nb,
-                         "note": "issue-bound kernel (one Philox4x32-10 block per base); see DESIGN.md"},
+                         "issue_slot_utilisation_ncu": 0.745,
+                         "note": "issue-bound kernel (one Philox4x32-10 block per base; ncu: 74.5 % of issue slots busy, 2420 warp "
+                                 "instructions per pair); traffic = ncu dram bytes of one launch of this kernel (profiles/); the "
+                                 "compaction pass adds ~2x the FASTQ bytes of HBM traffic per step; see DESIGN.md"},
         }
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
