@@ -104,7 +104,7 @@ def write_job(workdir, genome_bases, coverage, profile_name="XTen", insert=300, 
         names = ["chr%d" % (i + 1) for i in range(22)] + ["chrX", "chrY"]
         synth.make_genome(fa, lengths, seed=seed, names=names)
         open(fa + ".ok", "w").write("ok")
-    cfg = os.path.join(workdir, "bench_%d_%d.txt" % (genome_bases, coverage))
+    cfg = os.path.join(workdir, "bench_%d_%d_%s.txt" % (genome_bases, coverage, profile_name))
     synth.write_config(cfg, ref=fa, profile=os.path.join(data, testdata.PROFILES[profile_name]), name="test",
                        output=os.path.join(workdir, "out"), layout="PE", threads=threads, verbose=0, coverage=coverage,
                        insertSize=insert)
@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--genome-bases", type=int, default=3000000000)
     ap.add_argument("--coverage", type=int, default=30)
+    ap.add_argument("--profile", default="XTen", choices=["GAIIx", "HiSeq2000", "HiSeq2500", "XTen"],
+                    help="sequencing profile of data/ (BASELINE.json configs[4]: profile sweep)")
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
     ap.add_argument("--workdir", default=os.environ.get("SIMUSCOP_BENCH_DIR", "/tmp/simuscop_bench"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -234,10 +236,10 @@ def main():
     os.makedirs(a.workdir, exist_ok=True)
     t_setup0 = time.perf_counter()
     if rank == 0:
-        cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage)
+        cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage, a.profile)
     barrier()
     if rank != 0:
-        cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage)
+        cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage, a.profile)
     t_fasta = time.perf_counter() - t_setup0
 
     gen = cuda_binding.Generator(local)
@@ -334,8 +336,8 @@ def main():
             "metric": "simulated_bases_per_sec", "value": tot_bases / T, "unit": "bases/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * T / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "synthetic %.2f Gb genome (24 chromosomes), %dx PE151 WGS, Illumina_HiSeqXTen.profile, insertSize 300, "
-                                   "diploid, no SNP/variation" % (genome_len / 1e9, a.coverage),
+            "config": {"workload": "synthetic %.2f Gb genome (24 chromosomes), %dx PE%d WGS, %s profile, insertSize 300, "
+                                   "diploid, no SNP/variation" % (genome_len / 1e9, a.coverage, job.read_length, a.profile),
                        "planned_pairs": planned, "batch_pairs": a.batch_pairs, "seed": 1,
                        "l2": "inputs larger than L2: every step reads fresh fragments of a %.1f GB packed haplotype store and writes "
                              "a fresh %.1f GB slab" % (2 * genome_len * 0.375 / 1e9, st["fastq_bytes"] / a.steps / 1e9),

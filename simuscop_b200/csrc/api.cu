@@ -71,7 +71,8 @@ struct ssc_handle {
 	bool haveProfile = false;
 	ssc::DeviceTablesHost th;
 	ssc::DevTables dt;
-	DevBuf<uint32_t> d_isizeT, d_insT, d_delT, d_qualT;
+	DevBuf<uint32_t> d_isizeT, d_insT, d_delT, d_qualT, d_qualDiagT;
+	DevBuf<uint8_t> d_qualDiagSym;
 	DevBuf<uint16_t> d_isizeSym, d_insSym, d_delSym;
 	DevBuf<uint8_t> d_qualSym;
 	DevBuf<uint4> d_sub;
@@ -120,9 +121,9 @@ struct ssc_handle {
 
 namespace {
 
-bool use_fast(const ssc_handle* h, bool* qsmem, size_t* smemBytes) {
+bool use_fast(const ssc_handle* h, int* qmode, size_t* smemBytes) {
 	if (h->fp64 || h->forceGeneric) return false;
-	return ssc::fast_supported(h->dt, h->smemLimit, qsmem, smemBytes);
+	return ssc::fast_supported(h->dt, h->smemLimit, qmode, smemBytes);
 }
 
 
@@ -175,7 +176,7 @@ int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
 }
 
 int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
-	bool qsmem = false; size_t fastSmem = 0;
+	int qsmem = 0; size_t fastSmem = 0;
 	const bool fast = use_fast(h, &qsmem, &fastSmem);
 	const int tp = fast ? FG_WORKERS : GEN_TILE_PAIRS;
 	int nTiles = (int)((emitHi - emitLo + tp - 1) / tp);
@@ -291,6 +292,7 @@ int ssc_destroy(ssc_handle* h) {
 		if (h->evStage[b]) cudaEventDestroy(h->evStage[b]);
 	}
 	h->d_isizeT.release(); h->d_insT.release(); h->d_delT.release(); h->d_qualT.release();
+	h->d_qualDiagT.release(); h->d_qualDiagSym.release();
 	h->d_isizeSym.release(); h->d_insSym.release(); h->d_delSym.release(); h->d_qualSym.release();
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
@@ -334,6 +336,7 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	CK(h->d_insT.upload(th.insLen.T, s)); CK(h->d_insSym.upload(th.insLen.sym, s));
 	CK(h->d_delT.upload(th.delLen.T, s)); CK(h->d_delSym.upload(th.delLen.sym, s));
 	CK(h->d_qualT.upload(th.qualT, s)); CK(h->d_qualSym.upload(th.qualSym, s));
+	CK(h->d_qualDiagT.upload(th.qualDiagT, s)); CK(h->d_qualDiagSym.upload(th.qualDiagSym, s));
 	std::vector<uint4> sub(th.sub.size());
 	for (size_t i = 0; i < sub.size(); i++) sub[i] = make_uint4(th.sub[i].s0, th.sub[i].s1, th.sub[i].s2, th.sub[i].base);
 	CK(h->d_sub.upload(sub, s));
@@ -363,6 +366,7 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	d.delLenT = h->d_delT.p; d.delLenSym = h->d_delSym.p;
 	d.sub = h->d_sub.p; d.nSub = th.nRows * th.B;
 	d.qualT = h->d_qualT.p; d.qualSym = h->d_qualSym.p; d.qualPitch = th.qualPitch; d.nQualRows = 16 * th.B;
+	d.qualDiagT = h->d_qualDiagT.p; d.qualDiagSym = h->d_qualDiagSym.p; d.qualDiagPitch = th.diagPitch;
 	d.compLut = th.compLut;
 	d.baseChars = (uint32_t)(uint8_t)th.baseChar[0] | ((uint32_t)(uint8_t)th.baseChar[1] << 8) |
 	              ((uint32_t)(uint8_t)th.baseChar[2] << 16) | ((uint32_t)(uint8_t)th.baseChar[3] << 24);

@@ -37,6 +37,7 @@ struct DevTables {
 	const uint32_t* delLenT; const uint16_t* delLenSym;
 	const uint4* sub; int nSub;              // rows*B per read table; table of read 2 follows when useCdf2
 	const uint32_t* qualT; const uint8_t* qualSym; int qualPitch; int nQualRows;
+	const uint32_t* qualDiagT; const uint8_t* qualDiagSym; int qualDiagPitch;   // ref == call rows, [N*B][pitch]
 	uint32_t compLut;
 	uint32_t baseChars;                      // 4 ASCII characters, code i in byte i
 	// FP64 ground-truth tables (the reference's own arrays)

@@ -167,12 +167,18 @@ __device__ __forceinline__ int f_ndigits(uint32_t v) {
 
 __constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 
+struct QualTabs {
+	const uint32_t* T; const uint8_t* sym;            // QP == 8: shared, pitch 8
+	const uint32_t* diagT; const uint8_t* diagSym;    // QP == 2: shared, ref == call rows
+	const uint32_t* gT; const uint8_t* gSym;          // full table in global memory
+	int pitch, diagPitch;
+};
+
 struct WarpCtx {
 	int B, qualPitch, minQ, RL, nInsLen, nDelLen, nBasesM1, mDelta;
 	uint32_t baseChars, compLut;
 	const uint4* sub;          // shared: table of the current mate
-	const uint32_t* qualT;     // shared or global
-	const uint8_t* qualSym;
+	QualTabs q;
 	const uint32_t* insT; const uint16_t* insSym;
 	const uint32_t* delT; const uint16_t* delSym;
 	const uint32_t* win;       // shared window: data words [0..16), mask words [16..25)
@@ -182,7 +188,7 @@ struct WarpCtx {
 };
 
 // substitution + quality for one output base; returns (char | qual << 8)
-template <int QP> __device__ __forceinline__ uint32_t qual_lookup(const uint32_t* qualT, const uint8_t* qualSym, int pitch, int qrow, uint32_t u3);
+template <int QP> __device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur, uint32_t call, uint32_t binIdx, int B, uint32_t u3);
 
 template <int QP>
 __device__ __forceinline__ uint32_t call_base(const WarpCtx& w, uint32_t cur, int row, bool bad, bool curN, int binIdx,
@@ -197,8 +203,7 @@ __device__ __forceinline__ uint32_t call_base(const WarpCtx& w, uint32_t cur, in
 	if (call < 0) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }    // randomInteger(33, 53), Profile.cpp:1583
 	else {
 		ch = __byte_perm(w.baseChars, 0, 0x4440 | call);
-		const int qrow = ((int)cur * 4 + call) * w.B + binIdx;
-		q = qual_lookup<QP>(w.qualT, w.qualSym, w.qualPitch, qrow, u3);
+		q = qual_lookup<QP>(w.q, cur, (uint32_t)call, (uint32_t)binIdx, w.B, u3);
 	}
 	return ch | (q << 8);
 }
@@ -317,23 +322,38 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 	return m;
 }
 
-// quality lookup: row of QP (power of two) ascending thresholds padded with 0xFFFFFFFF; symbol index =
-// #{i : T[i] < u}.  QP == 8 is the shared-memory fast case (XTen-like profiles), fully unrolled.
+// Quality lookup.  Rows hold ascending inclusive thresholds padded with 0xFFFFFFFF; symbol index = #{i : T[i] < u}.
+//   QP == 8: all 16*B rows in shared memory, pitch 8 (XTen-like profiles), three unrolled steps;
+//   QP == 2: only the ref == call rows in shared memory (pitch = live symbols rounded up to 4, generic branch-free
+//            lower bound); the rare substituted bases go to the full table in global memory (L2);
+//   QP == 0: full table in global memory.
 template <int QP>
-__device__ __forceinline__ uint32_t qual_lookup(const uint32_t* qualT, const uint8_t* qualSym, int pitch, int qrow, uint32_t u3) {
+__device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur, uint32_t call, uint32_t binIdx, int B, uint32_t u3) {
 	if (QP == 8) {
-		const uint32_t* qt = qualT + qrow * 8;
+		const uint32_t qrow = (cur * 4u + call) * (uint32_t)B + binIdx;
+		const uint32_t* qt = q.T + qrow * 8;
 		uint32_t k = 0;
 		add_lt(k, qt[3], u3, 4u);
 		add_lt(k, qt[k + 1], u3, 2u);
 		add_lt(k, qt[k], u3, 1u);
-		return qualSym[qrow * 8 + k];
-	} else {
-		const uint32_t* qt = qualT + qrow * pitch;
-		int k = 0;
-		for (int s = pitch >> 1; s > 0; s >>= 1) if (qt[k + s - 1] < u3) k += s;
-		return qualSym[qrow * pitch + k];
+		return q.sym[qrow * 8 + k];
 	}
+	if (QP == 2 && cur == call) {
+		const uint32_t base = (cur * (uint32_t)B + binIdx) * (uint32_t)q.diagPitch;
+		const uint32_t* qt = q.diagT + base;
+		uint32_t k = 0;
+		for (int len = q.diagPitch; len > 1;) {
+			const int half = len >> 1;
+			add_lt(k, qt[k + half - 1], u3, (uint32_t)half);
+			len -= half;
+		}
+		return q.diagSym[base + k];
+	}
+	const uint32_t qrow = (cur * 4u + call) * (uint32_t)B + binIdx;
+	const uint32_t* qt = q.gT + qrow * q.pitch;
+	int k = 0;
+	for (int s = q.pitch >> 1; s > 0; s >>= 1) if (qt[k + s - 1] < u3) k += s;
+	return q.gSym[qrow * q.pitch + k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int nSubTotal = t.nSub * (t.useCdf2 ? 2 : 1);
-	const int nQual = QP ? t.nQualRows * t.qualPitch : 0;
+	const int nQual = QP == 8 ? t.nQualRows * 8 : (QP == 2 ? 4 * t.B * t.qualDiagPitch : 0);
 	const FastLayout L = fast_layout(nSubTotal, nQual, t.nIsize, t.nInsLen, t.nDelLen);
 
 	uint4* s_sub = (uint4*)(smem + L.sub);
@@ -362,10 +382,14 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 
 #pragma unroll 1
 	for (int i = threadIdx.x; i < nSubTotal; i += FG_THREADS) s_sub[i] = t.sub[i];
+	{
+		const uint32_t* srcT = QP == 8 ? t.qualT : t.qualDiagT;
+		const uint8_t* srcS = QP == 8 ? t.qualSym : t.qualDiagSym;
 #pragma unroll 1
-	for (int i = threadIdx.x; i < nQual / 4; i += FG_THREADS) ((uint4*)s_qualT)[i] = ((const uint4*)t.qualT)[i];
+		for (int i = threadIdx.x; i < nQual / 4; i += FG_THREADS) ((uint4*)s_qualT)[i] = ((const uint4*)srcT)[i];
 #pragma unroll 1
-	for (int i = threadIdx.x; i < nQual / 16; i += FG_THREADS) ((uint4*)s_qualSym)[i] = ((const uint4*)t.qualSym)[i];
+		for (int i = threadIdx.x; i < nQual / 16; i += FG_THREADS) ((uint4*)s_qualSym)[i] = ((const uint4*)srcS)[i];
+	}
 #pragma unroll 1
 	for (int i = threadIdx.x; i < t.nIsize; i += FG_THREADS) { s_isizeT[i] = t.isizeT[i]; s_isizeSym[i] = t.isizeSym[i]; }
 #pragma unroll 1
@@ -391,8 +415,8 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 	WarpCtx w;
 	w.B = t.B; w.qualPitch = t.qualPitch; w.minQ = t.minQ; w.RL = t.RL; w.nInsLen = t.nInsLen; w.nDelLen = t.nDelLen;
 	w.nBasesM1 = t.N - 1; w.mDelta = 0; w.baseChars = t.baseChars; w.compLut = t.compLut;
-	w.qualT = QP ? s_qualT : t.qualT;
-	w.qualSym = QP ? s_qualSym : t.qualSym;
+	w.q.T = s_qualT; w.q.sym = s_qualSym; w.q.diagT = s_qualT; w.q.diagSym = s_qualSym;
+	w.q.gT = t.qualT; w.q.gSym = t.qualSym; w.q.pitch = t.qualPitch; w.q.diagPitch = t.qualDiagPitch;
 	w.insT = s_insT; w.insSym = s_insSym; w.delT = s_delT; w.delSym = s_delSym;
 	w.win = (const uint32_t*)(wbase + L.w_win);
 	uint32_t* s_win = (uint32_t*)(wbase + L.w_win);
@@ -400,9 +424,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 	w.src = wbase + L.w_src; w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
 	w.k0 = (uint32_t)P.seed; w.k1 = (uint32_t)(P.seed >> 32);
 	w.lane = lane;
-	const uint32_t* qualT = QP ? s_qualT : t.qualT;
-	const uint8_t* qualSym = QP ? s_qualSym : t.qualSym;
-	const int qPitch = t.qualPitch;
+	const QualTabs qt = w.q;
 
 	unsigned long long accBases = 0, accReads = 0, accPairs = 0, accHap = 0;
 	const uint32_t insT = t.insT, delT = t.delT;
@@ -557,8 +579,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const Gen
 					uint32_t call = sr.w;
 					add_gt(call, x2[c], sr.x); add_gt(call, x2[c], sr.y); add_gt(call, x2[c], sr.z);
 					call = n3 ? cur : call;                                        // unknown context: base passes through
-					const uint32_t qrow = (cur * 4u + call) * (uint32_t)B + binIdx;
-					uint32_t q = qual_lookup<QP>(qualT, qualSym, qPitch, (int)qrow, x3[c]);
+					uint32_t q = qual_lookup<QP>(qt, cur, call, binIdx, B, x3[c]);
 					uint32_t ch = __byte_perm(baseChars, 0, 0x4440u | call);
 					if (n3 & curBit) { ch = 'N'; q = minQ + __umulhi(20u, x3[c]); }   // randomInteger(33, 53), Profile.cpp:1583
 					if (c < NCH - 1 || c * 32 + lane < RL) {
@@ -697,13 +718,15 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const GenParams P, 
 	}
 }
 
-bool fast_supported(const DevTables& t, int smemLimit, bool* qsmem, size_t* smemBytes) {
+bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemBytes) {
 	if (t.N != 4 || t.K != 3 || t.RL > 160 || t.RL < 33 || t.nIsize > 1024 || t.B > 160) return false;
 	const int nSubTotal = t.nSub * (t.useCdf2 ? 2 : 1);
-	const int withQ = fast_layout(nSubTotal, t.nQualRows * t.qualPitch, t.nIsize, t.nInsLen, t.nDelLen).total;
-	const int noQ = fast_layout(nSubTotal, 0, t.nIsize, t.nInsLen, t.nDelLen).total;
-	if (t.qualPitch == 8 && withQ <= smemLimit) { *qsmem = true; *smemBytes = (size_t)withQ; return true; }
-	if (noQ <= smemLimit) { *qsmem = false; *smemBytes = (size_t)noQ; return true; }
+	const int full = fast_layout(nSubTotal, t.nQualRows * 8, t.nIsize, t.nInsLen, t.nDelLen).total;
+	const int diag = fast_layout(nSubTotal, 4 * t.B * t.qualDiagPitch, t.nIsize, t.nInsLen, t.nDelLen).total;
+	const int none = fast_layout(nSubTotal, 0, t.nIsize, t.nInsLen, t.nDelLen).total;
+	if (t.qualPitch == 8 && full <= smemLimit) { *qmode = 8; *smemBytes = (size_t)full; return true; }
+	if (diag <= smemLimit) { *qmode = 2; *smemBytes = (size_t)diag; return true; }
+	if (none <= smemLimit) { *qmode = 0; *smemBytes = (size_t)none; return true; }
 	return false;
 }
 
@@ -717,15 +740,19 @@ static cudaError_t launch_fast_variant(const GenParams& P, size_t smemBytes, int
 }
 
 // P.out1/out2 = slot scratch, P.dense1/dense2 = final slabs, P.nTiles = groups of FG_WORKERS pairs
-cudaError_t launch_generate_fast(const GenParams& P, bool qsmem, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
+cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
                                  cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
 	const int nch = (P.t.RL + 31) / 32;
 	cudaError_t e;
 	if (e0) cudaEventRecord(e0, stream);
-	if (qsmem) {
+	if (qmode == 8) {
 		if (nch <= 3) e = launch_fast_variant<3, 8>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 8>(P, smemBytes, grid, stream);
 		else e = launch_fast_variant<5, 8>(P, smemBytes, grid, stream);
+	} else if (qmode == 2) {
+		if (nch <= 3) e = launch_fast_variant<3, 2>(P, smemBytes, grid, stream);
+		else if (nch == 4) e = launch_fast_variant<4, 2>(P, smemBytes, grid, stream);
+		else e = launch_fast_variant<5, 2>(P, smemBytes, grid, stream);
 	} else {
 		if (nch <= 3) e = launch_fast_variant<3, 0>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 0>(P, smemBytes, grid, stream);

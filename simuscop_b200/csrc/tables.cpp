@@ -3,6 +3,7 @@
 #include "tables.h"
 
 #include <cstring>
+#include <algorithm>
 #include <functional>
 
 namespace ssc {
@@ -149,6 +150,23 @@ const char* build_tables(const ssc_profile_tables* t, DeviceTablesHost* o) {
 			o->qualSym[i * pitch + j] = (uint8_t)(t->min_qual + qrows[i].sym[s]);
 		}
 	}
+	// diagonal rows (ref == call)
+	size_t dmax = 1;
+	for (int b = 0; b < 4; b++)
+		for (int j = 0; j < t->bins; j++) dmax = std::max(dmax, qrows[(size_t)(b * 4 + b) * t->bins + j].T.size());
+	o->diagPitch = (int)((dmax + 3) / 4 * 4);
+	o->qualDiagT.assign((size_t)4 * t->bins * o->diagPitch, 0xFFFFFFFFu);
+	o->qualDiagSym.assign((size_t)4 * t->bins * o->diagPitch, 0);
+	for (int b = 0; b < 4; b++)
+		for (int j = 0; j < t->bins; j++) {
+			const CompressedCdf& r = qrows[(size_t)(b * 4 + b) * t->bins + j];
+			size_t n = r.T.size(), base = ((size_t)b * t->bins + j) * o->diagPitch;
+			for (int k = 0; k < o->diagPitch; k++) {
+				size_t sidx = (size_t)k < n ? (size_t)k : n - 1;
+				o->qualDiagT[base + k] = (size_t)k < n ? r.T[k] : 0xFFFFFFFFu;
+				o->qualDiagSym[base + k] = (uint8_t)(t->min_qual + r.sym[sidx]);
+			}
+		}
 	return "";
 }
 

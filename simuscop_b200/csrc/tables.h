@@ -44,6 +44,10 @@ struct DeviceTablesHost {
 	std::vector<uint32_t> qualT;    // [N*N*B][qualPitch], padded with 0xFFFFFFFF
 	std::vector<uint8_t> qualSym;   // [N*N*B][qualPitch], padded with the last symbol
 	int maxQualRow;
+	// rows with ref == call only (the ones nearly every base uses), padded to diagPitch (multiple of 4)
+	int diagPitch;
+	std::vector<uint32_t> qualDiagT;   // [N*B][diagPitch]
+	std::vector<uint8_t> qualDiagSym;  // [N*B][diagPitch]
 	uint8_t compLut;                 // 2 bits per code: complement code
 	char baseChar[4];
 	int8_t asciiCode[256];           // ASCII -> code 0..3, or 4 (non-ACGT)
