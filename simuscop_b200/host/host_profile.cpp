@@ -64,7 +64,9 @@ void ProfileModel::load(const std::string& path, Config& cfg) {
 	}
 	if (bases.empty() || binCount <= 0 || kmer <= 0 || readLength <= 0) die(1, "Error: malformed model file " + path);
 	// the profile header overrides the configuration (Profile.cpp:1000-1003); bins are capped by the read length (:184-188)
-	if (binCount > readLength) binCount = readLength;
+	// (the reference clamps bins to the read length in Profile::init but keeps parsing binCount rows into the smaller
+	//  matrices, Profile.cpp:1000-1108 -- heap corruption; we refuse such a profile instead)
+	if (binCount > readLength) die(1, "Error: malformed model file " + path + ": binCount larger than readLength");
 	cfg.str["bases"] = bases; cfg.num["kmer"] = kmer; cfg.num["bins"] = binCount; cfg.num["readLength"] = readLength;
 	N = (int)bases.length(); K = kmer; B = binCount; RL = readLength;
 	rows = 0;

@@ -56,3 +56,66 @@ def write_config(path, **kw):
         for k in kw:
             if k not in order and kw[k] is not None:
                 f.write("%s = %s\n" % (k, kw[k]))
+
+
+def write_profile(path, seed=1, bases="ACTG", kmer=3, read_length=100, bins=20, ins_rate=5e-4, del_rate=5e-4,
+                  n_ins=12, n_del=20, std_isize=30.0, n_live_qual=10, sub_rate=0.01, zero_rows=2, gc_std=0.15):
+    """Random .profile in the format of Profile::saveResults (lib/profile/Profile.cpp:1240-1365).
+
+    Deliberately nasty: zero-probability leading symbols, a few all-zero substitution rows (identity rule,
+    Profile.cpp:848-860), an all-zero quality row (-> '~'), unnormalised rows, arbitrary k-mer size."""
+    rng = np.random.default_rng(seed)
+    N = len(bases)
+
+    def kmers():
+        out = []
+        for pad in range(kmer - 1, -1, -1):
+            valid = kmer - pad
+            for v in range(N ** valid):
+                digs = []
+                x = v
+                for _ in range(valid):
+                    digs.append(x % N)
+                    x //= N
+                out.append("X" * pad + "".join(bases[d] for d in reversed(digs)))
+        return out
+    with open(path, "w") as f:
+        f.write("#model created by simuscop_b200.synth.write_profile seed %d\n#reads: synthetic\n\n" % seed)
+        f.write("bases: %s\nreadLength: %d\nbinCount: %d\nkmer: %d\n\n" % (bases, read_length, bins, kmer))
+        f.write("\n[Insert Rate]\n%g\n[Insert Frequency]\n" % ins_rate)
+        insf = np.concatenate([[0.0], rng.random(n_ins - 1)])
+        f.write("\t".join("%g" % x for x in insf / insf.sum()) + "\n")
+        f.write("\n[Deletion Rate]\n%g\n[Deletion Frequency]\n" % del_rate)
+        delf = np.concatenate([[0.0], rng.random(n_del - 1)])
+        f.write("\t".join("%g" % x for x in delf / delf.sum()) + "\n")
+        f.write("\n[Substitution Probs]\n")
+        names = kmers()
+        zero = set(rng.choice(len(names), size=min(zero_rows, len(names)), replace=False).tolist())
+        for ki, km in enumerate(names):
+            f.write("kmer: %s\n" % km)
+            last = bases.index(km[-1])
+            for r in range(2 * bins):
+                if ki in zero and r % 7 == 0:
+                    row = np.zeros(N)
+                else:
+                    row = rng.random(N) * sub_rate
+                    row[last] = 1.0 - row.sum() + row[last]
+                    if rng.random() < 0.15:
+                        row[int(rng.integers(0, N))] = 0.0       # zero-probability symbol (possibly a leading one)
+                    row *= rng.uniform(0.5, 3.0)                  # unnormalised on purpose
+                f.write("\t".join("%g" % x for x in row) + "\n")
+        f.write("\n[Base Quality Distribution]\n")
+        for bp in range(N * N):
+            f.write("basePairIndx: %d\n" % bp)
+            for r in range(bins):
+                row = np.zeros(94)
+                if not (bp == 5 and r == 1):                      # one all-zero row
+                    lo = int(rng.integers(0, 94 - n_live_qual))
+                    idx = rng.choice(np.arange(lo, min(94, lo + 2 * n_live_qual)), size=n_live_qual, replace=False)
+                    row[idx] = rng.random(n_live_qual) * rng.uniform(1, 1000)
+                f.write("\t".join("%g" % x for x in row) + "\n")
+        f.write("\n[Insert Size Standard Deviation]\n%g\n" % std_isize)
+        f.write("\n[Log Ratio Mean Value]\n")
+        for g in range(101):
+            f.write("%d\t%g\n" % (g, 1.0 + 0.3 * np.sin(g / 16.0) if 20 <= g <= 80 else 0.2))
+        f.write("\n[Log Ratio Standard Deviation]\n%g\n" % gc_std)

@@ -120,3 +120,39 @@ def test_cli_sharded_over_two_handles_is_byte_identical(built, workdir):
         outs[tag] = (helpers.read_file(os.path.join(out, "test_1.fq")), helpers.read_file(os.path.join(out, "test_2.fq")))
         assert sorted(os.listdir(out)) == ["test_1.fq", "test_2.fq"]
     assert outs["one"] == outs["three"] and len(outs["one"][0]) > 0
+
+
+@pytest.mark.parametrize("name", sorted(helpers.STRESS))
+def test_synthetic_profiles_cli_and_abi(name, built, workdir):
+    """Odd k-mer sizes / read lengths / indel rates / degenerate rows: reference == oracle == CUDA (whichever kernel
+    variant the configuration selects) == forced generic kernel, through the ABI and through the CLI."""
+    import glob
+    import os
+    import subprocess
+    from simuscop_b200 import cuda_binding, oracle_binding, paths, synth
+    scn = helpers.build_stress(name, workdir)
+    plans, out_ref = helpers.run_reference_philox(scn, tag="st")
+    plan = planfile.read_plan(plans[0])
+    r1p, r2p = helpers.sample_files(out_ref, plan, 0, scn)
+    r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
+    assert len(r1) > 10000
+    o1, o2, _ = oracle_binding.generate(plan, scn["seed"])
+    assert (o1, o2) == (r1, r2)
+    for opt in (None, "force_generic"):
+        g = cuda_binding.Generator(0)
+        try:
+            if opt:
+                g.set_option(opt, 1)
+            g.load_plan(plan, scn["seed"])
+            f1, f2 = g.generate()
+        finally:
+            g.close()
+        assert helpers.first_diff(f1, r1) == -1, (opt, helpers.first_diff(f1, r1))
+        assert helpers.first_diff(f2, r2) == -1, (opt, helpers.first_diff(f2, r2))
+    d = scn["dir"]
+    cfg = os.path.join(d, "cfg_cli.txt")
+    synth.write_config(cfg, output=os.path.join(d, "out_cli"), **scn["kw"])
+    r = subprocess.run([paths.SIMUREADS, cfg], env=dict(os.environ, SIMUSCOP_SEED=str(scn["seed"])), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for f in glob.glob(os.path.join(out_ref, "*.fq")):
+        assert helpers.read_file(f) == helpers.read_file(os.path.join(d, "out_cli", os.path.basename(f)))

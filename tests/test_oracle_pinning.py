@@ -75,3 +75,26 @@ def test_oracle_matches_live_instrumented_reference(name, built, workdir):
         # and the live run reproduces the committed hashes (the instrumented build is deterministic)
         assert hashlib.sha256(r1).hexdigest() == gold["samples"][i]["fq1_sha256"]
         assert hashlib.sha256(open(pf, "rb").read()).hexdigest() == gold["samples"][i]["plan_sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
+@pytest.mark.parametrize("name", sorted(helpers.STRESS))
+def test_oracle_and_host_on_synthetic_profiles(name, built, workdir):
+    """Synthetic profiles with odd k-mer sizes, short/long reads, heavy indels, degenerate rows: the oracle and the
+    C++ front end's plan (tables included) against the live instrumented reference."""
+    import glob
+    import subprocess
+    from simuscop_b200 import paths, synth
+    scn = helpers.build_stress(name, workdir)
+    plans, out = helpers.run_reference_philox(scn, tag="st")
+    plan = planfile.read_plan(plans[0])
+    r1p, r2p = helpers.sample_files(out, plan, 0, scn)
+    f1, f2, info = oracle_binding.generate(plan, scn["seed"])
+    assert f1 == helpers.read_file(r1p) and f2 == helpers.read_file(r2p) and info["emitted"] > 100
+    d = scn["dir"]
+    cfg = os.path.join(d, "cfg_plan.txt")
+    synth.write_config(cfg, output=os.path.join(d, "out_plan"), **scn["kw"])
+    env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_DUMP_PLAN=os.path.join(d, "plan_ours"), SIMUSCOP_PLAN_ONLY="1")
+    r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(os.path.join(d, "plan_ours.0.plan"), "rb").read() == open(plans[0], "rb").read()
