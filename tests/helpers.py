@@ -33,15 +33,19 @@ SCENARIOS["se_mini"] = dict(lengths=[30000], profile="GAIIx", layout="SE", cover
 STRESS = {
     "k2_short": dict(profile_kw=dict(kmer=2, read_length=40, bins=40, ins_rate=2e-3, del_rate=2e-3), layout="PE", insertSize=120),
     "k4_long": dict(profile_kw=dict(kmer=4, read_length=200, bins=25, ins_rate=3e-3, del_rate=3e-3, n_ins=40, n_del=50, n_live_qual=30), layout="PE", insertSize=400),
-    "k3_indel_heavy": dict(profile_kw=dict(kmer=3, read_length=120, bins=30, ins_rate=2e-2, del_rate=2e-2, n_ins=30, n_del=30), layout="PE", insertSize=260),
+    "k3_indel_heavy": dict(profile_kw=dict(kmer=3, read_length=120, bins=30, ins_rate=6e-3, del_rate=8e-3, n_ins=12, n_del=30), layout="PE", insertSize=260),
     "k3_fixed_insert_se": dict(profile_kw=dict(kmer=3, read_length=64, bins=16, std_isize=0.0, n_live_qual=40), layout="SE", insertSize=150),
     "k3_fixed_insert_pe": dict(profile_kw=dict(kmer=3, read_length=90, bins=50, std_isize=0.0, n_live_qual=6, bases="GATC"), layout="PE", insertSize=200),
     "k1_tcga": dict(profile_kw=dict(kmer=1, read_length=151, bins=50, bases="TCGA", n_live_qual=7), layout="PE", insertSize=300),
 }
 
 
+# beyond the documented per-read limits: must fail loudly, never diverge silently
+OVERFLOW = dict(profile_kw=dict(kmer=3, read_length=120, bins=30, ins_rate=2e-2, del_rate=2e-2, n_ins=30, n_del=30), layout="PE", insertSize=260)
+
+
 def build_stress(name, workdir, seed=5):
-    sc = STRESS[name]
+    sc = OVERFLOW if name == "overflow" else STRESS[name]
     d = os.path.join(workdir, "stress_" + name)
     os.makedirs(d, exist_ok=True)
     synth.make_genome(os.path.join(d, "ref.fa"), [60000, 9000], seed=31, n_runs=2, lower_runs=1, run_len=200)

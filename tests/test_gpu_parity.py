@@ -156,3 +156,23 @@ def test_synthetic_profiles_cli_and_abi(name, built, workdir):
     assert r.returncode == 0, r.stderr[-2000:]
     for f in glob.glob(os.path.join(out_ref, "*.fq")):
         assert helpers.read_file(f) == helpers.read_file(os.path.join(d, "out_cli", os.path.basename(f)))
+
+
+def test_reads_beyond_the_scratch_limits_fail_loudly(built, workdir):
+    """A profile with 2 % insertion AND deletion rates outgrows the per-read limits (32 events / 128 inserted bases):
+    the library must return SSC_ERR_OVERFLOW, not a silently different FASTQ."""
+    from simuscop_b200 import cuda_binding
+    scn = helpers.build_stress("overflow", workdir)
+    plans, out_ref = helpers.run_reference_philox(scn, tag="ov")
+    plan = planfile.read_plan(plans[0])
+    for opt in (None, "force_generic"):
+        g = cuda_binding.Generator(0)
+        try:
+            if opt:
+                g.set_option(opt, 1)
+            g.load_plan(plan, scn["seed"])
+            with pytest.raises(cuda_binding.SscError) as e:
+                g.generate()
+            assert "ssc error 6" in str(e.value)
+        finally:
+            g.close()
