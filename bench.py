@@ -235,16 +235,19 @@ def main():
     barrier()
     os.makedirs(a.workdir, exist_ok=True)
     t_setup0 = time.perf_counter()
+    job = None
     if rank == 0:
         cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage, a.profile)
+        t_fasta = time.perf_counter() - t_setup0
+        job = host_binding.Job(cfg, 1)          # also writes the .fai next to the FASTA, once
     barrier()
     if rank != 0:
         cfg, genome_len = write_job(a.workdir, a.genome_bases, a.coverage, a.profile)
-    t_fasta = time.perf_counter() - t_setup0
+        t_fasta = time.perf_counter() - t_setup0
+        job = host_binding.Job(cfg, 1)
 
     gen = cuda_binding.Generator(local)
     gen.set_option("batch_pairs", a.batch_pairs)
-    job = host_binding.Job(cfg, 1)
     t0 = time.perf_counter()
     planned, emitted = job.prepare(0, gen)
     t_plan = time.perf_counter() - t0

@@ -146,12 +146,17 @@ void Fasta::open(const std::string& path) {
 		}
 		if (have) ents.push_back(cur);
 		std::stable_sort(ents.begin(), ents.end(), [](const FastaEntry& a, const FastaEntry& b) { return a.offset < b.offset; });
-		std::ofstream out(fai.c_str());
-		if (!out.is_open()) die(1, "could not open index file " + fai + " for writing!");
-		for (auto& e : ents) {
-			std::string nm = split(e.name, ' ').empty() ? "" : split(e.name, ' ')[0];
-			out << nm << "\t" << e.length << "\t" << e.offset << "\t" << e.line_blen << "\t" << e.line_len << std::endl;
+		// written under a private name and renamed, so that concurrent processes never read a partial index
+		const std::string tmp = fai + ".tmp." + std::to_string((long)getpid());
+		{
+			std::ofstream out(tmp.c_str());
+			if (!out.is_open()) die(1, "could not open index file " + fai + " for writing!");
+			for (auto& e : ents) {
+				std::string nm = split(e.name, ' ').empty() ? "" : split(e.name, ' ')[0];
+				out << nm << "\t" << e.length << "\t" << e.offset << "\t" << e.line_blen << "\t" << e.line_len << std::endl;
+			}
 		}
+		if (rename(tmp.c_str(), fai.c_str()) != 0) die(1, "could not open index file " + fai + " for writing!");
 	}
 	std::ifstream in(fai.c_str());
 	if (!in.is_open()) die(1, "could not open index file " + fai);
