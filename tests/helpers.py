@@ -26,6 +26,10 @@ SCENARIOS = {
                      insertSize=250, tumor=True),
 }
 
+# triploid genome with copy-number changes, and a haploid single-end run
+SCENARIOS["pe_ploidy3"] = dict(lengths=[2600000], names=["chr20"], profile="XTen", layout="PE", coverage=2, insertSize=300,
+                               variation=True, ploidy=3, n_runs=1)
+SCENARIOS["se_ploidy1"] = dict(lengths=[700000, 300000], profile="HiSeq2500", layout="SE", coverage=3, insertSize=200, ploidy=1)
 SCENARIOS["se_mini"] = dict(lengths=[30000], profile="GAIIx", layout="SE", coverage=2, insertSize=250, n_runs=1)
 
 # synthetic profiles (simuscop_b200.synth.write_profile): odd k-mer sizes, short / long reads, heavy indel rates,
@@ -96,6 +100,8 @@ def build_scenario(name, workdir, seed=7):
     kw = dict(ref=os.path.join(d, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[sc["profile"]]),
               layout=sc["layout"], coverage=sc["coverage"], insertSize=sc["insertSize"], threads=1, verbose=0,
               name="test")
+    if sc.get("ploidy"):
+        kw["ploidy"] = sc["ploidy"]
     if sc.get("variation"):
         with open(os.path.join(d, "variations.txt"), "w") as f:
             f.write(VARIATION_SMALL)

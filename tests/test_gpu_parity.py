@@ -16,7 +16,7 @@ def gen(built):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor"])
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor", "pe_ploidy3", "se_ploidy1"])
 def test_fastq_bit_exact_vs_instrumented_reference(name, gen, workdir):
     scn = helpers.build_scenario(name, workdir)
     plans, out = helpers.run_reference_philox(scn)

@@ -61,7 +61,7 @@ def test_oracle_pair_ranges_concatenate(built, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
-@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_wes"])
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_wes", "pe_ploidy3", "se_ploidy1"])
 def test_oracle_matches_live_instrumented_reference(name, built, workdir):
     scn = helpers.build_scenario(name, workdir)
     plans, out = helpers.run_reference_philox(scn, tag="pin")
