@@ -107,8 +107,8 @@ struct ssc_handle {
 	DevBuf<unsigned long long> d_tileState[2];
 	DevBuf<unsigned int> d_ticket[2];
 	uint8_t* d_slots[2] = {nullptr, nullptr};   // pass-1 scratch of the fast kernel (one set, stream ordered)
-	DevBuf<uint32_t> d_slotLens;
 	DevBuf<unsigned int> d_ticket2;
+	DevBuf<unsigned long long> d_blobPrefix;
 	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
 	ssc::BatchResult* h_result[2] = {nullptr, nullptr};
 
@@ -148,8 +148,8 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 		for (int f = 0; f < 2; f++) { if (h->d_slots[f]) cudaFree(h->d_slots[f]); h->d_slots[f] = nullptr; }
 		h->slabPairs = pairs; h->slabCap = cap;
 		for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_slots[f], (size_t)pairs * FG_SLOT + 64));
-		CK(h->d_slotLens.alloc((size_t)pairs));
 		CK(h->d_ticket2.alloc(1));
+		CK(h->d_blobPrefix.alloc((size_t)(pairs / 16) + 2));
 		int nTiles = (int)(pairs / 16) + 2;   // enough for every kernel's tile size
 		for (int b = 0; b < 2; b++) {
 			for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_out[b][f], cap));
@@ -178,11 +178,12 @@ int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
 int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	int qsmem = 0; size_t fastSmem = 0;
 	const bool fast = use_fast(h, &qsmem, &fastSmem);
-	const int tp = fast ? FG_WORKERS : GEN_TILE_PAIRS;
+	const int tp = fast ? FG_CHUNK : GEN_TILE_PAIRS;
 	int nTiles = (int)((emitHi - emitLo + tp - 1) / tp);
 	cudaStream_t s = h->compute;
 	CK(cudaMemsetAsync(h->d_tileState[buf].p, 0, sizeof(unsigned long long) * nTiles, s));
 	CK(cudaMemsetAsync(h->d_ticket[buf].p, 0, sizeof(unsigned int), s));
+	CK(cudaMemsetAsync(h->d_ticket2.p, 0, sizeof(unsigned int), s));
 	CK(cudaMemsetAsync(h->d_result[buf], 0, sizeof(ssc::BatchResult), s));
 	CK(ssc::launch_locate(h->d_emitBase.p, h->nDevBins, emitLo, tp, nTiles, h->d_tileStart[buf].p, s));
 	ssc::GenParams P;
@@ -190,18 +191,25 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	P.hap2 = h->d_hap2.p; P.hapN = h->d_hapN.p;
 	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
 	P.riskyAttempt = h->d_risky.p; P.names = h->d_names.p;
-	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi;
+	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi; P.one = 1;
+	P.insLim = h->dt.insEnable ? h->dt.insT + 1u : 0u;
+	P.delLim = h->dt.delEnable ? h->dt.delT + 1u : 0u;
+	P.alwaysSlow = (h->dt.insEnable && h->dt.insT == 0xFFFFFFFFu) || (h->dt.delEnable && h->dt.delT == 0xFFFFFFFFu);
+	for (int r = 0; r < 10; r++) {
+		P.rk[2 * r] = (uint32_t)h->seed + (uint32_t)r * 0x9E3779B9u;
+		P.rk[2 * r + 1] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+	}
 	P.tileStartBin = h->d_tileStart[buf].p; P.nTiles = nTiles;
-	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p;
+	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p; P.ticket2 = h->d_ticket2.p; P.blobPrefix = h->d_blobPrefix.p;
 	P.out1 = h->d_out[buf][0]; P.out2 = h->d_out[buf][1];
 	P.cap1 = h->slabCap; P.cap2 = h->slabCap;
 	P.result = h->d_result[buf];
 	int grid = std::min(nTiles, h->smCount);
 	if (fast) {
+		grid = std::min((nTiles + FG_GEN - 1) / FG_GEN, h->smCount);
 		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
-		P.slotLens = h->d_slotLens.p;
 		cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 		if (h->timeKernels) {
 			while ((int)h->kev.size() < h->kevUsed + 3) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }
@@ -209,7 +217,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			h->kevUsed += 3;
 		}
 		CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, e2));
-		h->stats.launches += 1;
+		h->stats.launches += 2;
 	} else {
 		ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
 		if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
@@ -297,7 +305,7 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
 	h->d_hap2.release(); h->d_hapN.release();
-	h->d_slotLens.release(); h->d_ticket2.release();
+	h->d_ticket2.release(); h->d_blobPrefix.release();
 	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
 	for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
 	if (h->evStart) cudaEventDestroy(h->evStart);

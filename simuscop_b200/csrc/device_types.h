@@ -64,14 +64,19 @@ struct GenParams {
 	const uint16_t* riskyAttempt;
 	const char* names;
 	uint64_t seed;
+	uint32_t rk[20];            // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
+	uint32_t insLim, delLim;    // fast kernel: candidate tests as u < limit (0 = disabled)
+	int alwaysSlow;             // a rate of 1 (limit 2^32) sends every read down the slow path
+	uint32_t one;               // 1, opaque to the compiler (see fadd_gt in gen_fast.cu)
 	int64_t emitLo, emitHi;    // emitted-pair index range of this batch
 	const int32_t* tileStartBin;
 	int nTiles;
 	unsigned long long* tileState;
+	unsigned long long* blobPrefix;   // fast kernel: exclusive prefix of the blob lengths (pass 2)
 	unsigned int* ticket;
+	unsigned int* ticket2;      // fast kernel: work counter of pass 1 (tickets of FG_CHUNK pairs)
 	uint8_t* out1; uint8_t* out2;       // generic kernel: final slabs; fast kernel: slot scratch
 	uint8_t* dense1; uint8_t* dense2;   // fast kernel: final slabs (pass 2)
-	uint32_t* slotLens;                 // fast kernel: len1 | len2 << 16 per slot
 	unsigned long long cap1, cap2;
 	BatchResult* result;
 };

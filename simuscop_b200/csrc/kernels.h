@@ -11,9 +11,13 @@
 #define GEN_TILE_PAIRS (GEN_WARPS * GEN_PPW)
 
 #ifndef FG_WORKERS
-#define FG_WORKERS 24                             /* independent warps per CTA of the fast kernel (one pair each) */
+#define FG_WORKERS 32                             /* warps per CTA of the fast kernel */
 #endif
+#define FG_GEN FG_WORKERS
 #define FG_THREADS (FG_WORKERS * 32)
+#ifndef FG_CHUNK
+#define FG_CHUNK 32                               /* consecutive pairs a warp of the fast kernel takes per ticket */
+#endif
 #define FG_SLOT 640                               /* bytes of HBM scratch per record (>= 96 + 2*256 + 4) */
 #define SSC_GPAD 64                               /* zero bases in front of the haplotype store */
 

@@ -28,6 +28,7 @@ for r in range(reps):
     res = g.generate_device()
     st = g.stats()
     tot = res["bytes1"] + res["bytes2"] + st["hap_bytes"]
-    print("rep %d: %.3f ms  %.1f Gbases/s  fastq %.1f GB/s  algorithmic %.1f GB/s (%.1f%% of 6554)  launches %d" % (
+    print("rep %d: %.3f ms  %.1f Gbases/s  fastq %.1f GB/s  algorithmic %.1f GB/s (%.1f%% of 6554)  launches %d  gen %.3f ms/batch  pass2 %.3f ms/batch" % (
         r, res["device_ms"], res["bases"] / res["device_ms"] / 1e6, (res["bytes1"] + res["bytes2"]) / res["device_ms"] / 1e6,
-        tot / res["device_ms"] / 1e6, 100 * tot / res["device_ms"] / 1e6 / 6554.2, st["launches"]))
+        tot / res["device_ms"] / 1e6, 100 * tot / res["device_ms"] / 1e6 / 6554.2, st["launches"],
+        st["gen_kernel_ms"] / max(1, st["timed_batches"]), st["compact_kernel_ms"] / max(1, st["timed_batches"])))
