@@ -86,7 +86,7 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 
 __host__ __device__ inline void fast_qual_bytes(const DevTables& t, int qp, int* qualBytes, int* qualSymBytes) {
 	if (qp == 8) { *qualBytes = t.nQualRows * F_QROW; *qualSymBytes = 0; }
-	else if (qp == 2) { *qualBytes = 4 * t.B * t.qualDiagPitch * 4; *qualSymBytes = 4 * t.B * t.qualDiagPitch; }
+	else if (qp == 2) { *qualBytes = 4 * t.B * (t.qualDiagPitch + 1) * 4; *qualSymBytes = 4 * t.B * (t.qualDiagPitch + 1); }   // odd word pitch
 	else { *qualBytes = 0; *qualSymBytes = 0; }
 }
 
@@ -233,7 +233,7 @@ __device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur,
 		return qa[k + 4];
 	}
 	if (QP == 2 && cur == call) {
-		const uint32_t base = (cur * (uint32_t)B + binIdx) * (uint32_t)q.diagPitch;
+		const uint32_t base = (cur * (uint32_t)B + binIdx) * (uint32_t)(q.diagPitch + 1);   // rows padded to an odd pitch (banks)
 		const uint32_t* qt = q.diagT + base;
 		uint32_t k = 0;
 		for (int len = q.diagPitch; len > 1;) {
@@ -537,9 +537,11 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		}
 	} else if (QP == 2) {
 #pragma unroll 1
-		for (int i = threadIdx.x; i < qualBytes / 16; i += FG_THREADS) ((uint4*)s_qual)[i] = ((const uint4*)t.qualDiagT)[i];
-#pragma unroll 1
-		for (int i = threadIdx.x; i < qualSymBytes / 16; i += FG_THREADS) ((uint4*)s_qualSym)[i] = ((const uint4*)t.qualDiagSym)[i];
+		for (int i = threadIdx.x; i < 4 * B * t.qualDiagPitch; i += FG_THREADS) {
+			const int r = i / t.qualDiagPitch, k = i - r * t.qualDiagPitch;
+			((uint32_t*)s_qual)[r * (t.qualDiagPitch + 1) + k] = t.qualDiagT[i];
+			s_qualSym[r * (t.qualDiagPitch + 1) + k] = t.qualDiagSym[i];
+		}
 	}
 #pragma unroll 1
 	for (int i = threadIdx.x; i < t.nIsize; i += FG_THREADS) { s_isizeT[i] = t.isizeT[i]; s_isizeSym[i] = t.isizeSym[i]; }
@@ -839,19 +841,22 @@ static cudaError_t launch_fast_variant(const GenParams& P, size_t smemBytes, int
 // P.out1/out2 = blob scratch, P.dense1/dense2 = final slabs, P.nTiles = tickets of FG_CHUNK pairs
 cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
                                  cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
-	const int nch = (P.t.RL + 31) / 32;
+	const int nch = (P.t.RL + 31) / 32;   // the kernel's chunk count is exact: only the last chunk has idle lanes
 	cudaError_t e;
 	if (e0) cudaEventRecord(e0, stream);
 	if (qmode == 8) {
-		if (nch <= 3) e = launch_fast_variant<3, 8>(P, smemBytes, grid, stream);
+		if (nch <= 2) e = launch_fast_variant<2, 8>(P, smemBytes, grid, stream);
+		else if (nch == 3) e = launch_fast_variant<3, 8>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 8>(P, smemBytes, grid, stream);
 		else e = launch_fast_variant<5, 8>(P, smemBytes, grid, stream);
 	} else if (qmode == 2) {
-		if (nch <= 3) e = launch_fast_variant<3, 2>(P, smemBytes, grid, stream);
+		if (nch <= 2) e = launch_fast_variant<2, 2>(P, smemBytes, grid, stream);
+		else if (nch == 3) e = launch_fast_variant<3, 2>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 2>(P, smemBytes, grid, stream);
 		else e = launch_fast_variant<5, 2>(P, smemBytes, grid, stream);
 	} else {
-		if (nch <= 3) e = launch_fast_variant<3, 0>(P, smemBytes, grid, stream);
+		if (nch <= 2) e = launch_fast_variant<2, 0>(P, smemBytes, grid, stream);
+		else if (nch == 3) e = launch_fast_variant<3, 0>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 0>(P, smemBytes, grid, stream);
 		else e = launch_fast_variant<5, 0>(P, smemBytes, grid, stream);
 	}

@@ -41,6 +41,17 @@ STRESS = {
     "k3_fixed_insert_se": dict(profile_kw=dict(kmer=3, read_length=64, bins=16, std_isize=0.0, n_live_qual=40), layout="SE", insertSize=150),
     "k3_fixed_insert_pe": dict(profile_kw=dict(kmer=3, read_length=90, bins=50, std_isize=0.0, n_live_qual=6, bases="GATC"), layout="PE", insertSize=200),
     "k1_tcga": dict(profile_kw=dict(kmer=1, read_length=151, bins=50, bases="TCGA", n_live_qual=7), layout="PE", insertSize=300),
+    # fast-kernel edge cases: read lengths around the 32-cycle chunk boundaries (the record terminators ride on the idle
+    # lanes of the last chunk only when RL % 32 is in 1..29), the longest / shortest supported reads, <= 7 live quality
+    # symbols (all quality rows in shared memory) and a name that makes the record header longer than one / two warps
+    "k3_rl95": dict(profile_kw=dict(kmer=3, read_length=95, bins=50, n_live_qual=7), layout="PE", insertSize=220),
+    "k3_rl126": dict(profile_kw=dict(kmer=3, read_length=126, bins=33, n_live_qual=5, ins_rate=1e-3), layout="PE", insertSize=280),
+    "k3_rl160": dict(profile_kw=dict(kmer=3, read_length=160, bins=50, n_live_qual=7, bases="CATG"), layout="PE", insertSize=330),
+    "k3_rl33": dict(profile_kw=dict(kmer=3, read_length=33, bins=11, n_live_qual=7), layout="SE", insertSize=80),
+    "k3_long_name": dict(profile_kw=dict(kmer=3, read_length=100, bins=20, n_live_qual=7), layout="PE", insertSize=250,
+                         name="population_with_a_rather_long_name_0123456789"),
+    "k3_longer_name": dict(profile_kw=dict(kmer=3, read_length=75, bins=50, n_live_qual=12), layout="PE", insertSize=200,
+                           name="p" * 55),
 }
 
 
@@ -56,7 +67,7 @@ def build_stress(name, workdir, seed=5):
     prof = os.path.join(d, "synthetic.profile")
     synth.write_profile(prof, seed=sum(map(ord, name)), **sc["profile_kw"])
     kw = dict(ref=os.path.join(d, "ref.fa"), profile=prof, layout=sc["layout"], coverage=8, insertSize=sc["insertSize"],
-              threads=1, verbose=0, name="s")
+              threads=1, verbose=0, name=sc.get("name", "s"))
     return dict(dir=d, kw=kw, seed=seed, name=name)
 
 
