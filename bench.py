@@ -328,9 +328,10 @@ def main():
         nb = max(1, st["timed_batches"])
         gen_ms = st["gen_kernel_ms"] / nb
         achieved = alg_bytes / nb / (gen_ms / 1000.0) / 1e9 if gen_ms > 0 else 0.0
-        traffic = None
+        traffic, issue, ipp = None, None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["generate_slots_kernel"]
+            issue, ipp = tr.get("issue_slot_utilisation"), tr.get("warp_instructions_per_pair")
             if tr["batch_pairs"] == a.batch_pairs:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except Exception:
@@ -354,12 +355,13 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "generate_slots_kernel",
-                         "kernel_ms_per_launch": gen_ms, "compact_kernel_ms_per_launch": st["compact_kernel_ms"] / nb,
+                         "kernel_ms_per_launch": gen_ms, "pass2_ms_per_launch": st["compact_kernel_ms"] / nb,
                          "algorithmic_bytes_per_launch": alg_bytes / nb,
-                         "issue_slot_utilisation_ncu": 0.745,
-                         "note": "issue-bound kernel (one Philox4x32-10 block per base; ncu: 74.5 % of issue slots busy, 2420 warp "
-                                 "instructions per pair); traffic = ncu dram bytes of one launch of this kernel (profiles/); the "
-                                 "compaction pass adds ~2x the FASTQ bytes of HBM traffic per step; see DESIGN.md"},
+                         "issue_slot_utilisation_ncu": issue, "warp_instructions_per_pair_ncu": ipp,
+                         "note": "issue-bound kernel, not HBM-bound: one Philox4x32-10 block per base (4 draws) plus ~25 table / compare "
+                                 "instructions; ncu figures from profiles/ (traffic = dram bytes of one launch of this kernel); pass 2 "
+                                 "(scan + move of the per-ticket blobs to the dense ordered slab) adds ~2x the FASTQ bytes of HBM traffic "
+                                 "per step at ~80 % of the copy bandwidth; see DESIGN.md"},
         }
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1

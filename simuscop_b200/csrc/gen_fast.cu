@@ -440,27 +440,51 @@ __device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, in
 	if (lane < len - t0) dst[t0 + lane] = __ldcg(src + t0 + lane);
 }
 
-// pass 2a: exclusive prefix of the packed blob lengths (len1 << 31 | len2; a slab holds < 2^31 bytes), one CTA
+// pass 2a: exclusive prefix of the packed blob lengths (len1 << 31 | len2; a slab holds < 2^31 bytes), one CTA,
+// rounds of SC_THREADS * 8 lengths (each thread 64 contiguous bytes), warp-shuffle scans
 static constexpr int SC_THREADS = 1024;
 __global__ void __launch_bounds__(SC_THREADS) scan_blobs_kernel(const GenParams P) {
-	__shared__ unsigned long long s_part[SC_THREADS];
+	__shared__ unsigned long long s_warp[SC_THREADS / 32];
+	__shared__ unsigned long long s_carry;
 	const int n = P.nTiles;
-	const int per = (n + SC_THREADS - 1) / SC_THREADS;
-	const int lo = threadIdx.x * per, hi = min(n, lo + per);
-	unsigned long long sum = 0;
-	for (int i = lo; i < hi; i++) sum += P.tileState[i];
-	s_part[threadIdx.x] = sum;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
 	__syncthreads();
-	for (int d = 1; d < SC_THREADS; d <<= 1) {
-		unsigned long long v = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0ull;
+	for (int base = 0; base < n; base += SC_THREADS * 8) {
+		const int i0 = base + threadIdx.x * 8;
+		unsigned long long v[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? P.tileState[i0 + k] : 0ull;
+		unsigned long long sum = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) sum += v[k];
+		unsigned long long incl = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) incl += o;
+		}
+		if (lane == 31) s_warp[warp] = incl;
 		__syncthreads();
-		s_part[threadIdx.x] += v;
+		if (warp == 0) {
+			unsigned long long w = s_warp[lane];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d);
+				if (lane >= d) w += o;
+			}
+			s_warp[lane] = w;                     // inclusive prefix of the warp totals
+		}
+		__syncthreads();
+		unsigned long long run = s_carry + (warp ? s_warp[warp - 1] : 0ull) + incl - sum;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { if (i0 + k < n) P.blobPrefix[i0 + k] = run; run += v[k]; }
+		__syncthreads();
+		if (threadIdx.x == SC_THREADS - 1) s_carry = run;
 		__syncthreads();
 	}
-	unsigned long long run = s_part[threadIdx.x] - sum;
-	for (int i = lo; i < hi; i++) { const unsigned long long v = P.tileState[i]; P.blobPrefix[i] = run; run += v; }
-	if (threadIdx.x == SC_THREADS - 1) {
-		const unsigned long long fin = s_part[SC_THREADS - 1];
+	if (threadIdx.x == 0) {
+		const unsigned long long fin = s_carry;
 		P.result->bytes1 = fin >> 31;
 		P.result->bytes2 = fin & 0x7fffffffull;
 		if ((fin >> 31) > P.cap1 || (fin & 0x7fffffffull) > P.cap2) atomicOr(&P.result->errorFlags, 1u);
