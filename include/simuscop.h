@@ -152,6 +152,15 @@ int ssc_genome_reserve(ssc_handle* h, uint64_t total_bases);
 int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* first_base);
 int ssc_genome_size(ssc_handle* h, uint64_t* n_bases);
 
+/* GC census of haplotype-store intervals: the device half of the GC-weighted read plan
+ * (Segment::getWeightedLength, lib/segment/Segment.cpp:567-624, which calls calculateGCPercent,
+ * lib/mydefine/MyDefine.cpp:279-303, once per 1 kb window / capture target).  For interval i =
+ * store bases [starts[i], starts[i]+lens[i]) (lens[i] >= 0, inside the appended store) it returns
+ * gc[i] = number of G or C bases and nn[i] = number of non-ACGT bases; the caller forms the
+ * reference's integer percentage (nn > 0 ? -1 : 100*gc/len).  Host arrays, copied inside. */
+int ssc_gc_census(ssc_handle* h, const int64_t* starts, const int32_t* lens, int64_t n,
+                  int32_t* gc, int32_t* nn);
+
 /* Uploads the plan, runs the fragment census (failCount > 1000 rule, Segment.cpp:753-762)
  * for `seed`, and computes pair / fragCount prefix sums.  *planned_pairs = number of pair
  * IDs (PE: sum ceil(read_count/2); SE: sum read_count). */

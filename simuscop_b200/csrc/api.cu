@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -109,6 +110,8 @@ struct ssc_handle {
 	uint8_t* d_slots[2] = {nullptr, nullptr};   // pass-1 scratch of the fast kernel (one set, stream ordered)
 	DevBuf<unsigned int> d_ticket2;
 	DevBuf<unsigned long long> d_blobPrefix;
+	DevBuf<int64_t> d_cenStarts;                  // ssc_gc_census scratch (grow-only)
+	DevBuf<int32_t> d_cenLens, d_cenGc, d_cenNn;
 	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
 	ssc::BatchResult* h_result[2] = {nullptr, nullptr};
 
@@ -306,6 +309,7 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
 	h->d_hap2.release(); h->d_hapN.release();
 	h->d_ticket2.release(); h->d_blobPrefix.release();
+	h->d_cenStarts.release(); h->d_cenLens.release(); h->d_cenGc.release(); h->d_cenNn.release();
 	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
 	for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
 	if (h->evStart) cudaEventDestroy(h->evStart);
@@ -434,6 +438,40 @@ int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* fi
 int ssc_genome_size(ssc_handle* h, uint64_t* n_bases) {
 	if (!h || !n_bases) return fail(SSC_ERR_INVALID, "null argument");
 	*n_bases = h->genomeSize;
+	return SSC_OK;
+}
+
+int ssc_gc_census(ssc_handle* h, const int64_t* starts, const int32_t* lens, int64_t n, int32_t* gc, int32_t* nn) {
+	if (!h || n < 0 || (n && (!starts || !lens || !gc || !nn))) return fail(SSC_ERR_INVALID, "null argument");
+	if (!h->haveProfile || !h->d_hap2.p) return fail(SSC_ERR_STATE, "ssc_genome_append must precede ssc_gc_census");
+	if (n == 0) return SSC_OK;
+	if (n > 0x7fffffffLL * 8) return fail(SSC_ERR_INVALID, "too many intervals");
+	CK(cudaSetDevice(h->device));
+	for (int64_t i = 0; i < n; i++)
+		if (starts[i] < 0 || lens[i] < 0 || (uint64_t)(starts[i] + lens[i]) > h->genomeSize)
+			return fail(SSC_ERR_INVALID, "interval %lld outside the haplotype store", (long long)i);
+	uint32_t gcCodes = 0;
+	for (int k = 0; k < 4; k++) if (h->th.baseChar[k] == 'G' || h->th.baseChar[k] == 'C') gcCodes |= 1u << k;
+	cudaStream_t s = h->compute;
+	const bool timing = getenv("SIMUSCOP_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = now();
+	if (timing) { cudaStreamSynchronize(s); fprintf(stderr, "[simuscop timing] gc_census: drained the upload queue in %.3f s\n", now() - t0); t0 = now(); }
+	// census buffers live in the handle and only grow (a cudaMalloc/cudaFree pair per call stalls for up to 0.7 s)
+	DevBuf<int64_t>& d_starts = h->d_cenStarts; DevBuf<int32_t>& d_lens = h->d_cenLens; DevBuf<int32_t>& d_gc = h->d_cenGc; DevBuf<int32_t>& d_nn = h->d_cenNn;
+	if (d_starts.n < (size_t)n) {
+		const size_t cap = (size_t)n + (size_t)n / 2 + 1024;
+		CK(d_starts.alloc(cap)); CK(d_lens.alloc(cap)); CK(d_gc.alloc(cap)); CK(d_nn.alloc(cap));
+	}
+	CK(cudaMemcpyAsync(d_starts.p, starts, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(d_lens.p, lens, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+	CK(ssc::launch_gc_census(h->d_hap2.p, h->d_hapN.p, d_starts.p, d_lens.p, n, gcCodes, d_gc.p, d_nn.p, s));
+	CK(cudaMemcpyAsync(gc, d_gc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(nn, d_nn.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (timing) fprintf(stderr, "[simuscop timing] gc_census: %lld intervals in %.3f s\n", (long long)n, now() - t0);
+	h->stats.launches += 1;
+	h->stats.h2d_bytes += (uint64_t)n * 12; h->stats.d2h_bytes += (uint64_t)n * 8;
 	return SSC_OK;
 }
 

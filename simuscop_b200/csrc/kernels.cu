@@ -93,6 +93,52 @@ __global__ void pack_kernel(const uint8_t* __restrict__ ascii, uint64_t n, uint6
 }
 
 // ----------------------------------------------------------------------------------------
+// gc_census_kernel: G/C and non-ACGT base counts of store intervals (one warp per interval),
+// the device half of Segment::getWeightedLength -> calculateGCPercent (Segment.cpp:567-624,
+// MyDefine.cpp:279-303).  A lane takes groups of 32 bases: two data words + one mask word.
+// gcCodes: bit k set iff 2-bit code k is G or C in the profile's base order.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {   // bit i of the low half -> bit 2i
+	x &= 0xffffu;
+	x = (x | (x << 8)) & 0x00FF00FFu;
+	x = (x | (x << 4)) & 0x0F0F0F0Fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	x = (x | (x << 1)) & 0x55555555u;
+	return x;
+}
+__device__ __forceinline__ uint32_t gc_fields(uint32_t w, uint32_t gcCodes) {   // bit 2i set iff base i of the word is G or C
+	const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+	uint32_t ind = 0;
+	if (gcCodes & 1u) ind |= ~lo & ~hi;
+	if (gcCodes & 2u) ind |= lo & ~hi;
+	if (gcCodes & 4u) ind |= ~lo & hi;
+	if (gcCodes & 8u) ind |= lo & hi;
+	return ind & 0x55555555u;
+}
+__global__ void gc_census_kernel(const uint32_t* __restrict__ hap2, const uint32_t* __restrict__ hapN,
+                                 const int64_t* __restrict__ starts, const int32_t* __restrict__ lens, int64_t n,
+                                 uint32_t gcCodes, int32_t* __restrict__ gc, int32_t* __restrict__ nn) {
+	const int lane = threadIdx.x & 31;
+	const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (i >= n) return;
+	const int64_t a = starts[i] + SSC_GPAD, b = a + lens[i];
+	int cgc = 0, cn = 0;
+	for (int64_t g = (a >> 5) + lane; (g << 5) < b; g += 32) {
+		const int64_t g0 = g << 5;
+		const int lo = a > g0 ? (int)(a - g0) : 0, hi = b < g0 + 32 ? (int)(b - g0) : 32;
+		uint32_t m = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+		m &= ~((1u << lo) - 1u);
+		const uint32_t nm = hapN[g] & m;
+		cn += __popc(nm);
+		const uint32_t v = m & ~nm;                                   // valid ACGT bases (non-ACGT are stored as code 0)
+		cgc += __popc(gc_fields(hap2[2 * g], gcCodes) & spread16(v)) + __popc(gc_fields(hap2[2 * g + 1], gcCodes) & spread16(v >> 16));
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) { cgc += __shfl_xor_sync(0xffffffffu, cgc, d); cn += __shfl_xor_sync(0xffffffffu, cn, d); }
+	if (lane == 0) { gc[i] = cgc; nn[i] = cn; }
+}
+
+// ----------------------------------------------------------------------------------------
 // one fragment attempt (Segment.cpp:743-762): start position, wanted length, clipped length
 // ----------------------------------------------------------------------------------------
 template <bool FP64>
@@ -682,6 +728,15 @@ cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, 
 	int blocks = (nBins + threads - 1) / threads;
 	if (fp64) census_kernel<true><<<blocks, threads, 0, stream>>>(t, bins, nBins, seed, riskyAttempt, emitted);
 	else census_kernel<false><<<blocks, threads, 0, stream>>>(t, bins, nBins, seed, riskyAttempt, emitted);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_gc_census(const uint32_t* hap2, const uint32_t* hapN, const int64_t* starts, const int32_t* lens, int64_t n,
+                             uint32_t gcCodes, int32_t* gc, int32_t* nn, cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	const int threads = 256;
+	const int64_t blocks = (n + threads / 32 - 1) / (threads / 32);
+	gc_census_kernel<<<(unsigned)blocks, threads, 0, stream>>>(hap2, hapN, starts, lens, n, gcCodes, gc, nn);
 	return cudaGetLastError();
 }
 

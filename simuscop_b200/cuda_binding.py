@@ -11,7 +11,7 @@ from . import abi
 from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
-           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_set_plan", "ssc_generate",
+           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
            "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host"]
 
 _lib = None
@@ -33,6 +33,7 @@ def lib():
         L.ssc_genome_reserve.argtypes = [C.c_void_p, C.c_uint64]
         L.ssc_genome_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ssc_genome_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ssc_gc_census.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ssc_set_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.ssc_generate.argtypes = [C.c_void_p, C.c_int64, C.c_int64, abi.SINK_FN, C.c_void_p]
@@ -85,6 +86,15 @@ class Generator:
         _ck(lib().ssc_genome_append(self.h, g.ctypes.data, g.size, C.byref(first)))
         assert first.value == 0
         self.set_plan(plan.bins, plan.segs, plan.names, seed)
+
+    def gc_census(self, starts, lens):
+        """G/C and non-ACGT base counts of haplotype-store intervals (ssc_gc_census)."""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        gc = np.zeros(len(starts), np.int32)
+        nn = np.zeros(len(starts), np.int32)
+        _ck(lib().ssc_gc_census(self.h, starts.ctypes.data, lens.ctypes.data, len(starts), gc.ctypes.data, nn.ctypes.data))
+        return gc, nn
 
     def set_plan(self, bins, segs, names, seed):
         bins = np.ascontiguousarray(bins)

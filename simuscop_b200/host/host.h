@@ -71,6 +71,12 @@ struct Snp { long long pos; char nucleotide; };
 struct Target { long spos, epos; };
 
 struct Bin { long spos, epos; int hap; double weight; int rc; };
+struct BinSpec { long spos, epos; int hap; int kind; long n; long gcStart, gcLen; };   // a bin before its GC draw (host_plan.cpp)
+struct ChrLayout {   // where the haplotype strings of one chromosome live in the device store
+	std::vector<std::vector<int64_t>> base;      // [segment][haplotype] store index of the string, -1 = absent
+	std::vector<std::vector<size_t>> hapLen;     // [segment][haplotype]
+	std::vector<int64_t> contigEnd;              // [haplotype]
+};
 
 struct Segment {
 	int idx; std::string chr; long start, end; int CN, mCN;
@@ -113,6 +119,11 @@ public:
 	// bins + weights (Segment::getWeightedLength, Segment.cpp:550-641)
 	double weighted_length(Segment& seg, const std::string& popu);
 	double weighted_length_from(Segment& seg, const std::vector<std::string>& haps);
+	void enumerate_bins(const Segment& seg, const std::vector<size_t>& hapLen, std::vector<BinSpec>& out);
+	double weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc);
+	// weights pass on the device (ssc_gc_census), streaming the haplotype store at the same time
+	int device_weights(const std::string& popu, const std::vector<ssc_handle*>& devs, uint64_t& localSize,
+	                   std::map<std::string, ChrLayout>& layout);
 	long long hapCacheBudget = 0;                             // bytes of haplotype strings that may stay cached
 	void set_read_counts(const std::string& popu, long reads);   // Genome::setReadCounts, Genome.cpp:783-825
 	void begin_plan();                                        // reads, ACNs, srand (Genome.cpp:831-852)

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 
@@ -207,6 +208,14 @@ static int gc_percent(const char* s, size_t n) {
 	return 100 * gc / (int)(n - nn);
 }
 
+namespace {
+// phase timers of the plan construction (printed when SIMUSCOP_TIMING is set)
+struct PhaseTimers {
+	double build = 0, gc = 0, upload = 0, counts = 0, census = 0, enumerate = 0;
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} g_tm;
+}  // namespace
+
 // Segment::getWeightedLength, lib/segment/Segment.cpp:550-641
 double Job::weighted_length(Segment& seg, const std::string& popu) {
 	double wl = 0;
@@ -215,8 +224,11 @@ double Job::weighted_length(Segment& seg, const std::string& popu) {
 		return wl;
 	}
 	std::vector<std::string> haps;
+	double t0 = PhaseTimers::now();
 	build_haplotypes(seg, popu, haps);
+	double t1 = PhaseTimers::now();
 	wl = weighted_length_from(seg, haps);
+	g_tm.build += t1 - t0; g_tm.gc += PhaseTimers::now() - t1;
 	// keep the strings for the materialisation pass when they fit the host budget (saves the second build)
 	size_t bytes = 0;
 	for (auto& h : haps) bytes += h.size();
@@ -224,54 +236,142 @@ double Job::weighted_length(Segment& seg, const std::string& popu) {
 	return wl;
 }
 
-double Job::weighted_length_from(Segment& seg, const std::vector<std::string>& haps) {
-	double wl = 0;
+// The bins of Segment::getWeightedLength (Segment.cpp:567-624) in the reference's order, without their weights:
+// bin = (spos, epos, haplotype), GC interval = bases [gcStart, gcStart + gcLen) of that haplotype string, and the
+// weight formula: kind 0: gcFactor / fragSize; kind 1: gcFactor * n / (fragSize * fragSize); kind 2: no draw, weight 0.
+void Job::enumerate_bins(const Segment& seg, const std::vector<size_t>& hapLen, std::vector<BinSpec>& out) {
 	const int ploidy = cfg.num["ploidy"];
 	const unsigned int fragSize = 1000;
+	out.clear();
 	if (targets.empty()) {
 		for (int i = 0; i < ploidy; i++) {
-			const std::string& p = haps[i];
-			if (p.empty()) continue;
-			size_t len = p.length();
+			const size_t len = hapLen[i];
+			if (len == 0) continue;
 			int k = (int)(len / fragSize);
 			for (int j = 0; j < k; j++) {
 				long spos = (long)j * fragSize, epos = (long)(j + 1) * fragSize - 1;
-				int gc = gc_percent(p.data() + spos, fragSize);
-				double w = prof.gc_factor(gc) / fragSize;
-				seg.bins.push_back(Bin{spos, epos, i, w, 0});
-				wl += w;
+				out.push_back(BinSpec{spos, epos, i, 0, 0, spos, (long)fragSize});
 			}
 			if ((size_t)k * fragSize < len) {
 				long spos = (long)k * fragSize;
-				int gc = gc_percent(p.data() + spos, len - (size_t)spos);
-				double w = prof.gc_factor(gc) * (len - (size_t)spos) / (fragSize * fragSize);
-				seg.bins.push_back(Bin{spos, (long)len - 1, i, w, 0});
-				wl += w;
+				out.push_back(BinSpec{spos, (long)len - 1, i, 1, (long)(len - (size_t)spos), spos, (long)(len - (size_t)spos)});
 			}
 		}
 	} else if (!seg.targetIdx.empty()) {
 		const std::vector<Target>& tg = targets[seg.chr];
 		for (int i = 0; i < ploidy; i++) {
-			const std::string& p = haps[i];
-			if (p.empty()) continue;
+			const size_t len = hapLen[i];
+			if (len == 0) continue;
 			int n = ((int)seg.seqReps.size() < ploidy) ? 1 : seg.seqReps[i];
-			long refLen = (long)(p.length() / n);
+			long refLen = (long)(len / n);
 			for (int k = 0; k < n; k++)
 				for (int m : seg.targetIdx) {
 					long spos = std::max(tg[m].spos, seg.start) - seg.start;
 					long epos = std::min(tg[m].epos, seg.start + refLen - 1) - seg.start;
-					long sk = spos + (long)(k * p.length() / n), ek = epos + (long)(k * p.length() / n);
-					int gc = gc_percent(p.data() + sk, ek >= sk ? (size_t)(ek - sk + 1) : 0);
-					double w = prof.gc_factor(gc) * (ek - sk + 1) / (fragSize * fragSize);
-					seg.bins.push_back(Bin{sk, ek, i, w, 0});
-					wl += w;
+					long sk = spos + (long)(k * len / n), ek = epos + (long)(k * len / n);
+					out.push_back(BinSpec{sk, ek, i, 1, ek - sk + 1, sk, ek >= sk ? ek - sk + 1 : 0});
 				}
 		}
 	} else {
-		seg.bins.push_back(Bin{0, 0, 0, 0.0, 0});
+		out.push_back(BinSpec{0, 0, 0, 2, 0, 0, 0});
+	}
+}
+
+// weights of the enumerated bins from their GC percentages (one Profile::getGCFactor draw per bin, in bin order)
+double Job::weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc) {
+	const unsigned int fragSize = 1000;
+	double wl = 0;
+	for (size_t b = 0; b < specs.size(); b++) {
+		const BinSpec& sp = specs[b];
+		double w;
+		if (sp.kind == 0) w = prof.gc_factor(gc[b]) / fragSize;
+		else if (sp.kind == 1) w = prof.gc_factor(gc[b]) * sp.n / (fragSize * fragSize);
+		else w = 0.0;
+		seg.bins.push_back(Bin{sp.spos, sp.epos, sp.hap, w, 0});
+		wl += w;
 	}
 	seg.weighted = !seg.bins.empty();
 	return wl;
+}
+
+double Job::weighted_length_from(Segment& seg, const std::vector<std::string>& haps) {
+	std::vector<size_t> hapLen(haps.size());
+	for (size_t i = 0; i < haps.size(); i++) hapLen[i] = haps[i].length();
+	std::vector<BinSpec> specs;
+	enumerate_bins(seg, hapLen, specs);
+	std::vector<int> gc(specs.size());
+	for (size_t b = 0; b < specs.size(); b++)
+		gc[b] = specs[b].kind == 2 ? 0 : gc_percent(haps[specs[b].hap].data() + specs[b].gcStart, (size_t)specs[b].gcLen);
+	return weights_from_gc(seg, specs, gc.data());
+}
+
+// Device mode of the weights pass: the haplotype strings of one population are built chromosome by chromosome, appended
+// to the haplotype store(s) in contig order (for every haplotype index, the segments' strings in order) and dropped; the
+// GC percentages of all bins of the chromosome come from ssc_gc_census on the packed store.  Same bins, same draws in
+// the same order, hence the same weights as weighted_length_from() -- and no haplotype string outlives its chromosome.
+int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>& devs, uint64_t& localSize,
+                        std::map<std::string, ChrLayout>& layout) {
+	const int ploidy = cfg.num["ploidy"];
+	int rc = 0;
+	for (auto& chr : chroms) {
+		std::vector<Segment>& v = segs[popu][chr];
+		ChrLayout& L = layout[chr];
+		L.base.assign(v.size(), std::vector<int64_t>(ploidy, -1));
+		L.hapLen.assign(v.size(), std::vector<size_t>(ploidy, 0));
+		L.contigEnd.assign(ploidy, 0);
+		double t0 = PhaseTimers::now();
+		std::vector<std::vector<std::string>> haps(v.size());
+		for (size_t k = 0; k < v.size(); k++) {
+			build_haplotypes(v[k], popu, haps[k]);
+			for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = haps[k][h].size();
+		}
+		double t1 = PhaseTimers::now();
+		for (int h = 0; h < ploidy; h++) {
+			for (size_t k = 0; k < v.size(); k++) {
+				if (haps[k][h].empty()) continue;
+				uint64_t first = localSize;
+				for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
+				L.base[k][h] = (int64_t)first;
+				localSize = first + haps[k][h].size();
+			}
+			L.contigEnd[h] = (int64_t)localSize;
+		}
+		haps.clear(); haps.shrink_to_fit();
+		double t2 = PhaseTimers::now();
+		// census of every bin of the chromosome in one call
+		std::vector<std::vector<BinSpec>> specs(v.size());
+		std::vector<int64_t> starts; std::vector<int32_t> lens;
+		for (size_t k = 0; k < v.size(); k++) {
+			if (v[k].weighted) continue;
+			enumerate_bins(v[k], L.hapLen[k], specs[k]);
+			for (auto& sp : specs[k]) {
+				if (sp.kind == 2) continue;
+				starts.push_back(L.base[k][sp.hap] + sp.gcStart);
+				lens.push_back((int32_t)sp.gcLen);
+			}
+		}
+		std::vector<int32_t> cgc(starts.size()), cnn(starts.size());
+		g_tm.enumerate += PhaseTimers::now() - t2;
+		rc = ssc_gc_census(devs[0], starts.data(), lens.data(), (int64_t)starts.size(), cgc.data(), cnn.data());
+		if (rc) return rc;
+		double t3 = PhaseTimers::now();
+		size_t q = 0;
+		std::vector<int> gc;
+		for (size_t k = 0; k < v.size(); k++) {
+			if (v[k].weighted) continue;
+			gc.assign(specs[k].size(), 0);
+			for (size_t b = 0; b < specs[k].size(); b++) {
+				if (specs[k][b].kind == 2) continue;
+				// calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303: empty -> 0, any N -> -1, else 100*gc/n (integer)
+				const int32_t n = lens[q];
+				gc[b] = n == 0 ? 0 : (cnn[q] > 0 ? -1 : 100 * cgc[q] / n);
+				q++;
+			}
+			weights_from_gc(v[k], specs[k], gc.data());
+		}
+		g_tm.build += t1 - t0; g_tm.upload += t2 - t1; g_tm.census += t3 - t2; g_tm.gc += PhaseTimers::now() - t3;
+	}
+	return 0;
 }
 
 // Genome::setReadCounts + Segment::setReadCount, lib/genome/Genome.cpp:783-825, lib/segment/Segment.cpp:462-476
@@ -397,24 +497,32 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 	std::vector<ssc_bin> bins;
 	std::vector<ssc_segment> segments;
 	std::string names;
+	const bool onDevice = !devs.empty();
 	for (auto& pp : pops) {
 		const std::string& popu = pp.first;
+		// device mode: weights pass = haplotype upload + GC census on the GPU; plan-only mode: host strings
+		std::map<std::string, ChrLayout> layout;
+		if (onDevice) { rc = device_weights(popu, devs, localSize, layout); if (rc) return rc; }
+		double tc0 = PhaseTimers::now();
 		set_read_counts(popu, pp.second);
+		g_tm.counts += PhaseTimers::now() - tc0;
 		for (auto& chr : chroms) {
 			std::vector<Segment>& v = segs[popu][chr];
 			const int32_t nameOff = (int32_t)names.size();
 			const std::string nm = "@" + popu + "#" + chr + "#";
 			names += nm;
-			// materialise the chromosome's haplotypes (Genome.cpp:876-878)
+			// the chromosome's haplotype strings (Genome.cpp:876-878): needed here in plan-only mode and for a plan dump
 			std::vector<std::vector<std::string>> haps(v.size());
-			for (size_t k = 0; k < v.size(); k++) {
-				if (!v[k].hapCache.empty()) {     // kept from the weights pass (same strings: generateSegSequences is deterministic once mIndx is set)
-					size_t b = 0;
-					for (auto& h : v[k].hapCache) b += h.size();
-					haps[k].swap(v[k].hapCache);
-					v[k].hapCache.clear(); v[k].hapCache.shrink_to_fit();
-					hapCacheBudget += (long long)b;
-				} else build_haplotypes(v[k], popu, haps[k]);
+			if (!onDevice || pw.fp) {
+				for (size_t k = 0; k < v.size(); k++) {
+					if (!v[k].hapCache.empty()) {     // kept from the weights pass (same strings: generateSegSequences is deterministic once mIndx is set)
+						size_t bb = 0;
+						for (auto& h : v[k].hapCache) bb += h.size();
+						haps[k].swap(v[k].hapCache);
+						v[k].hapCache.clear(); v[k].hapCache.shrink_to_fit();
+						hapCacheBudget += (long long)bb;
+					} else build_haplotypes(v[k], popu, haps[k]);
+				}
 			}
 			if (pw.fp) {
 				std::string u;
@@ -423,22 +531,26 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 				pw.rec(2, u);
 			}
 			// contig layout: for every haplotype index, the segments' strings in order
-			std::vector<std::vector<int64_t>> base(v.size(), std::vector<int64_t>(ploidy, -1));
-			std::vector<int64_t> contigEnd(ploidy, 0);
-			for (int h = 0; h < ploidy; h++) {
-				for (size_t k = 0; k < v.size(); k++) {
-					if (haps[k][h].empty()) continue;
-					uint64_t first = localSize;
-					for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
-					base[k][h] = (int64_t)first;
-					localSize = first + haps[k][h].size();
+			ChrLayout hostLayout;
+			if (!onDevice) {
+				hostLayout.base.assign(v.size(), std::vector<int64_t>(ploidy, -1));
+				hostLayout.hapLen.assign(v.size(), std::vector<size_t>(ploidy, 0));
+				hostLayout.contigEnd.assign(ploidy, 0);
+				for (int h = 0; h < ploidy; h++) {
+					for (size_t k = 0; k < v.size(); k++) {
+						hostLayout.hapLen[k][h] = haps[k][h].size();
+						if (haps[k][h].empty()) continue;
+						hostLayout.base[k][h] = (int64_t)localSize;
+						localSize += haps[k][h].size();
+					}
+					hostLayout.contigEnd[h] = (int64_t)localSize;
 				}
-				contigEnd[h] = (int64_t)localSize;
 			}
+			const ChrLayout& L = onDevice ? layout[chr] : hostLayout;
 			for (size_t k = 0; k < v.size(); k++) {
 				Segment& sg = v[k];
 				uint64_t seqSize = 0;
-				for (int h = 0; h < ploidy; h++) seqSize += haps[k][h].size();
+				for (int h = 0; h < ploidy; h++) seqSize += L.hapLen[k][h];
 				const uint32_t segsize = (uint32_t)((unsigned int)seqSize / (unsigned int)sg.CN);   // Segment.cpp:712-714
 				ssc_segment ss;
 				ss.first_bin = (int64_t)bins.size(); ss.n_bins = (int64_t)sg.bins.size();
@@ -447,9 +559,9 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 				for (auto& b : sg.bins) {
 					ssc_bin sb;
 					memset(&sb, 0, sizeof(sb));
-					const bool present = b.hap >= 0 && b.hap < ploidy && base[k][b.hap] >= 0;
-					sb.hap_base = present ? base[k][b.hap] : 0;
-					sb.contig_end = present ? contigEnd[b.hap] : 0;
+					const bool present = b.hap >= 0 && b.hap < ploidy && L.base[k][b.hap] >= 0;
+					sb.hap_base = present ? L.base[k][b.hap] : 0;
+					sb.contig_end = present ? L.contigEnd[b.hap] : 0;
 					sb.spos = (int32_t)b.spos; sb.epos = (int32_t)b.epos;
 					sb.segsize = segsize;
 					sb.read_count = (present && sg.readCount != 0) ? b.rc : 0;   // Segment::yieldReads early return, Segment.cpp:675-677
@@ -474,6 +586,9 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 			}
 		}
 	}
+	if (getenv("SIMUSCOP_TIMING"))
+		fprintf(stderr, "[simuscop timing] haplotypes %.2f s, upload+pack %.2f s, gc census (device, incl. bin enumeration %.2f s) %.2f s, gc weights (host) %.2f s, read counts %.2f s\n",
+		        g_tm.build, g_tm.upload, g_tm.enumerate, g_tm.census, g_tm.gc, g_tm.counts);
 	if (pw.fp) { pw.rec(9, std::string()); fclose(pw.fp); }
 	if (devs.empty()) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
 	for (ssc_handle* dev : devs) {

@@ -176,3 +176,67 @@ def test_reads_beyond_the_scratch_limits_fail_loudly(built, workdir):
             assert "ssc error 6" in str(e.value)
         finally:
             g.close()
+
+
+def test_gc_census_matches_host_counts(built, workdir):
+    """ssc_gc_census (device half of Segment::getWeightedLength / calculateGCPercent) against numpy on the same
+    haplotype string: random, empty, single-base, word-straddling and whole-store intervals, N runs, lower case,
+    and a profile whose base order puts G on code 0 (the code non-ACGT bases are stored with)."""
+    import numpy as np
+    from simuscop_b200 import cuda_binding
+    rng = np.random.default_rng(11)
+    for stress in ("k3_rl95", "k3_fixed_insert_pe"):            # base orders ACTG and GATC
+        scn = helpers.build_stress(stress, workdir)
+        plans, _ = helpers.run_reference_philox(scn, tag="gc")
+        plan = planfile.read_plan(plans[0])
+        g = cuda_binding.Generator(0)
+        try:
+            g.load_plan(plan, scn["seed"])
+            hap = np.frombuffer(bytes(plan.genome), np.uint8)
+            n = len(hap)
+            up = hap & 0xDF                                      # upper case
+            is_gc = (up == ord("G")) | (up == ord("C"))
+            is_n = ~((up == ord("A")) | (up == ord("C")) | (up == ord("G")) | (up == ord("T")))
+            assert is_n.any()
+            cg = np.concatenate(([0], np.cumsum(is_gc & ~is_n)))
+            cn = np.concatenate(([0], np.cumsum(is_n)))
+            starts = rng.integers(0, n, 4000)
+            lens = np.minimum(rng.integers(0, 3000, 4000), n - starts)
+            starts = np.concatenate((starts, [0, 0, n - 1, n, 5, 31, 32, 33, 0]))
+            lens = np.concatenate((lens, [0, 1, 1, 0, 27, 1, 1, 64, n]))
+            # 1 kb windows exactly as the plan uses them
+            starts = np.concatenate((starts, np.arange(0, n - 1000, 1000)))
+            lens = np.concatenate((lens, np.full(len(np.arange(0, n - 1000, 1000)), 1000)))
+            gc, nn = g.gc_census(starts, lens)
+            assert (gc == cg[starts + lens] - cg[starts]).all()
+            assert (nn == cn[starts + lens] - cn[starts]).all()
+            with pytest.raises(cuda_binding.SscError):
+                g.gc_census([n - 3], [10])                       # interval past the store
+        finally:
+            g.close()
+
+
+def test_device_plan_equals_host_plan(built, workdir):
+    """The plan built with the GPU weights pass (haplotype upload + ssc_gc_census) is the plan of the host-only pass:
+    the CLI's plan dump with a device is byte-identical to the SIMUSCOP_PLAN_ONLY dump (which test_host_logic pins
+    against the instrumented reference), for WGS with variants, WES targets and a tumour mixture."""
+    import os
+    import subprocess
+    from simuscop_b200 import paths, synth
+    for name in ("pe_variants", "pe_wes", "se_tumor"):
+        scn = helpers.build_scenario(name, workdir)
+        d = scn["dir"]
+        dumps = {}
+        for tag, extra in (("host", {"SIMUSCOP_PLAN_ONLY": "1"}), ("dev", {})):
+            cfg = os.path.join(d, "cfg_plan_%s.txt" % tag)
+            synth.write_config(cfg, output=os.path.join(d, "out_plan_" + tag), **scn["kw"])
+            prefix = os.path.join(d, "plan_%s" % tag)
+            env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_DUMP_PLAN=prefix, **extra)
+            r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            files = sorted(f for f in os.listdir(d) if f.startswith("plan_%s" % tag))
+            assert files
+            dumps[tag] = [helpers.read_file(os.path.join(d, f)) for f in files]
+        assert len(dumps["host"]) == len(dumps["dev"])
+        for a, b in zip(dumps["host"], dumps["dev"]):
+            assert a == b
