@@ -495,6 +495,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	std::vector<int32_t> riskyBase(n_bins, -1);
 	int64_t riskyTotal = 0;
 	int maxName = 0;
+	if (names_len < 0 || names_len >= (1 << 17)) return fail(SSC_ERR_INVALID, "name blob of %lld bytes (limit 131071)", (long long)names_len);
 	for (int64_t s = 0; s < n_segs; s++) {
 		if (segs[s].first_bin < 0 || segs[s].n_bins < 0 || segs[s].first_bin + segs[s].n_bins > n_bins)
 			return fail(SSC_ERR_INVALID, "segment %lld: bin range out of bounds", (long long)s);

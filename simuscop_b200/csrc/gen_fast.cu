@@ -189,6 +189,13 @@ __device__ __forceinline__ int uni_lookup(const uint32_t* T, const uint16_t* sym
 	return (int)sym[lo];
 }
 
+__device__ __forceinline__ int f_ndigits(uint32_t v) {
+	int n = 1;
+	n += v >= 10u; n += v >= 100u; n += v >= 1000u; n += v >= 10000u; n += v >= 100000u;
+	n += v >= 1000000u; n += v >= 10000000u; n += v >= 100000000u; n += v >= 1000000000u;
+	return n;
+}
+
 // floor(v / 10^d) = umulhi(v, M) >> S for every v < 2^31 (checked exhaustively at the step boundaries)
 __constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 __constant__ uint32_t c_divM[10] = {0u, 0x66666667u, 0x51eb851fu, 0x10624dd3u, 0x68db8badu, 0x14f8b589u, 0x431bde83u, 0x6b5fca6bu,
@@ -210,6 +217,7 @@ struct WarpCtx {
 	const uint32_t* insT; const uint16_t* insSym;
 	const uint32_t* delT; const uint16_t* delSym;
 	const uint32_t* win;       // shared window: data words [0..16), mask words [16..25)
+	const uint8_t* lutB;       // shared: context LUT (16-bit entries, 6 variants of 64)
 	uint8_t* src; uint32_t* ev; uint8_t* insb;
 	const uint32_t* rk;        // Philox round keys
 	uint32_t c0, c1;           // pair counter words
@@ -363,19 +371,52 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 		} else cum -= el;
 	}
 	__syncwarp();
+	// ---- re-pack the post-indel read (2-bit codes + non-ACGT flags, 16 pad bases in front) so that the per-base work
+	// below is the fast path's: context cut out of packed words, LUT -> substitution row -> quality row
+	uint32_t* pk = (uint32_t*)w.insb;                // 18 words: the inserted bases are not needed any more
+	uint32_t* pkN = pk + 18;                         // 10 words
+	{
+		const uint32_t* s32 = (const uint32_t*)w.src;
+		const uint32_t a0 = s32[2 * lane], a1 = s32[2 * lane + 1];
+		// byte i of a word holds one base: gather the low two bits (code) / bit 2 (non-ACGT) of the four bytes by multiplication
+		const uint32_t c8 = (((a0 & 0x03030303u) * 0x01041040u) >> 24) | ((((a1 & 0x03030303u) * 0x01041040u) >> 24) << 8);
+		const uint32_t n8 = ((((a0 >> 2) & 0x01010101u) * 0x01020408u) >> 24) | (((((a1 >> 2) & 0x01010101u) * 0x01020408u) >> 24) << 4);
+		__syncwarp();                                // every lane has read its inserted bases / source bytes
+		((uint16_t*)pk)[2 + lane] = (uint16_t)c8;
+		((uint8_t*)pkN)[4 + lane] = (uint8_t)n8;
+		if (lane == 0) { pk[0] = 0u; pkN[0] = 0u; }
+	}
+	__syncwarp();
 	const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
 	const int chunksM = (m + 31) >> 5;
 	auto emit = [&](int j, uint32_t u2, uint32_t u3) {
-		const uint32_t cur = w.src[j];
-		const uint32_t p1 = j >= 1 ? w.src[j - 1] : 0u;
-		const uint32_t p2 = j >= 2 ? w.src[j - 2] : 0u;
-		const bool bad = ((cur | p1 | p2) & 4u) != 0;
-		const int row = j >= 2 ? (int)(20u + 16u * (p2 & 3u) + 4u * (p1 & 3u) + (cur & 3u))
-		                       : j == 1 ? (int)(4u + 4u * (p1 & 3u) + (cur & 3u)) : (int)(cur & 3u);
-		const int binIdx = (int)__umulhi((uint32_t)(j * w.B), inv);
-		const uint32_t r = call_base<QP>(w, cur & 3u, row, bad, (cur & 4u) != 0, binIdx, u2, u3);
-		stage[H + j] = (uint8_t)r;
-		stage[H + m + 3 + j] = (uint8_t)(r >> 8);
+		const int rb = 14 + j, nb = 30 + j;          // first of the three context bases / of their flags
+		const uint32_t v6 = __funnelshift_r(pk[rb >> 4], pk[(rb >> 4) + 1], (uint32_t)(rb & 15) * 2u) & 63u;
+		const uint32_t n3 = __funnelshift_r(pkN[nb >> 5], pkN[(nb >> 5) + 1], (uint32_t)(nb & 31)) & 7u;   // bit 2 = the base itself
+		const uint32_t var = j >= 2 ? 0u : (j == 0 ? 2u : 3u);                                            // 'X' padded contexts
+		const uint32_t rowIdx = *(const uint16_t*)(w.lutB + var * 128u + v6 * 2u);
+		const uint32_t binIdx = __umulhi((uint32_t)(j * w.B), inv);
+		const uint4 sr = w.sub[rowIdx + binIdx];
+		const uint32_t cur = v6 >> 4;
+		uint32_t acc = sr.w;
+		add_gt(acc, u2, sr.x, (uint32_t)F_QROW); add_gt(acc, u2, sr.y, (uint32_t)F_QROW); add_gt(acc, u2, sr.z, (uint32_t)F_QROW);
+		if (n3) acc = w.qualBaseS + cur * (5u * F_QROW);                       // unknown context: the base passes through
+		uint32_t ch, q;
+		if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
+		else if (QP == 8) {
+			uint32_t qa = binIdx * (16u * F_QROW) + acc;
+			add_lt(qa, lds_u32(qa + 24), u3, 32u);
+			add_lt(qa, lds_u32(qa + 8), u3, 16u);
+			add_lt(qa, lds_u32(qa), u3, 8u);
+			q = lds_u8(qa + 4);
+			ch = lds_u8(qa + 5);
+		} else {
+			const uint32_t r16 = acc / (uint32_t)F_QROW;                       // qualBaseS == 0 here
+			q = qual_lookup<QP>(w.q, r16 >> 2, r16 & 3u, binIdx, w.B, u3);
+			ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
+		}
+		stage[H + j] = (uint8_t)ch;
+		stage[H + m + 3 + j] = (uint8_t)q;
 	};
 #if SSC_SLOW_UNROLL
 	// the draws of the first NCH chunks are the caller's registers
@@ -630,6 +671,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	const uint32_t lutFwd0 = (lane == 0 ? 2u : (lane == 1 ? 3u : 0u)) * 128u;
 	const uint32_t lutRev0 = (lane == 0 ? 4u : (lane == 1 ? 5u : 1u)) * 128u;
 	const uint8_t* lutB = (const uint8_t*)s_lut;
+	w.lutB = lutB;
 	const uint32_t baseChars = t.baseChars;
 	const uint32_t one = P.one;
 
@@ -643,31 +685,42 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		if (lane == 0) chunk = (int)atomicAdd(P.ticket2, 1u);
 		chunk = __shfl_sync(0xffffffffu, chunk, 0);
 		if (chunk >= P.nTiles) break;
-		// slot = pair index inside the batch (a batch has < 2^31 / FG_SLOT pairs); bin ends are kept relative to the batch too
-		uint32_t slot = (uint32_t)chunk * FG_CHUNK;
+		// slot = pair index inside the batch (a batch has < 2^31 / FG_SLOT pairs)
+		const uint32_t slot0 = (uint32_t)chunk * FG_CHUNK;
+		const uint32_t nSlots = (uint32_t)(P.emitHi - P.emitLo);
+		const int count = (int)(slot0 + FG_CHUNK < nSlots ? FG_CHUNK : nSlots - slot0);
 		uint32_t acc = 0;                                // bases | haplotype bytes << 16 of this ticket
 		uint32_t pos1 = (uint32_t)chunk * (FG_CHUNK * FG_SLOT), pos2 = pos1;   // next free byte of this ticket's blobs (scratch < 2^32 bytes)
-		const uint32_t nSlots = (uint32_t)(P.emitHi - P.emitLo);
-		const uint32_t slotEnd = slot + FG_CHUNK < nSlots ? slot + FG_CHUNK : nSlots;
-		int b = P.tileStartBin[chunk];
-		auto rel_end = [&](int bb) { const int64_t d = P.emitBase[bb + 1] - P.emitLo; return d > 0x7fffffffLL ? 0x7fffffffu : (uint32_t)d; };
-		uint32_t binEnd = rel_end(b);
-#pragma unroll 1
-		for (; slot < slotEnd; slot++) {
-			while (slot >= binEnd) { b++; binEnd = rel_end(b); }
-			const DevBin bin = P.bins[b];
-			const int ord = (int)((int64_t)slot - (bin.emit_base - P.emitLo));
+
+		// ---- ticket prologue, lane-parallel: lane L prepares pair slot0 + L (bin, pair ID, fragment draw, header digit counts);
+		// the pair loop below fetches these by shuffle instead of every lane repeating the same scalar work for every pair
+		uint32_t k_pairLo, k_pairHi, k_fstartLo, k_fstartHi, k_flen, k_posmod, k_frag, k_name;
+		{
+			const uint32_t mySlot = slot0 + (uint32_t)(lane < count ? lane : count - 1);
+			const int b0 = P.tileStartBin[chunk];
+			// bin of my pair: bins hold >= 1 pair, so it is one of b0 .. b0+31; lane i looks at the first pair of bin b0+1+i
+			const int64_t probe = (int64_t)b0 + 1 + lane;
+			const int64_t startRel64 = probe <= P.nBins ? P.emitBase[probe] - P.emitLo : 0x7fffffffLL;
+			const uint32_t startRel = startRel64 > 0x7fffffffLL ? 0x7fffffffu : (uint32_t)startRel64;
+			int cnt = 0;                                 // number of those bins that start at or before my pair (starts ascend)
+#pragma unroll
+			for (int step = 16; step > 0; step >>= 1) {
+				const int tprobe = cnt + step - 1;
+				const uint32_t sv = __shfl_sync(0xffffffffu, startRel, tprobe & 31);
+				if (tprobe <= 30 && sv <= mySlot) cnt += step;
+			}
+			const DevBin bin = P.bins[b0 + cnt];
+			const int ord = (int)((int64_t)mySlot - (bin.emit_base - P.emitLo));
 			const uint64_t pair = (uint64_t)(bin.plan_base + ord);
 			const uint32_t fragCount = (uint32_t)(bin.frag_base + ord + 1);
 			uint32_t attempt = 0;
 			if (bin.risky_base >= 0) attempt = P.riskyAttempt[bin.risky_base + ord];
-			w.c0 = (uint32_t)pair; w.c1 = (uint32_t)(pair >> 32);
-			// ---- fragment (Segment.cpp:743-751)
-			const u32x4 fb = philox_rk(w.c0, w.c1, (uint32_t)STREAM_FRAG << 24, attempt, P.rk);
+			// fragment (Segment.cpp:743-751)
+			const u32x4 fb = philox_rk((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)STREAM_FRAG << 24, attempt, P.rk);
 			const long long pos = f_draw_pos(fb.x, bin.spos, bin.epos);
 			long long want;
 			if (!t.paired) want = (long long)bin.epos - bin.spos + 1;
-			else if (t.nIsize > 0) want = t.minIS + coop_lookup(s_isizeT, s_isizeSym, t.nIsize, fb.y, lane);
+			else if (t.nIsize > 0) want = t.minIS + uni_lookup(s_isizeT, s_isizeSym, t.nIsize, fb.y);
 			else want = t.fixedInsert;
 			const int64_t fstart = bin.hap_base + pos;
 			const long long avail = bin.contig_end - fstart;
@@ -675,13 +728,32 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			uint32_t posmod = (uint32_t)pos;                                             // pos % segsize: only copies past the first need the division
 			if (posmod >= bin.segsize) posmod %= bin.segsize;
 			const bool seReverse = (!t.paired) && ((fb.z >> 31) != 0);                   // randomInteger(0, 2) != 0
-			acc += min((uint32_t)((flen + 3) / 4 + (flen + 7) / 8), 2047u) << 16;                  // haplotype bytes of the ticket (statistics)
+			uint32_t hapB = lane < count ? min((uint32_t)((flen + 3) / 4 + (flen + 7) / 8), 2047u) : 0u;   // haplotype bytes (statistics)
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) hapB += __shfl_xor_sync(0xffffffffu, hapB, d);
+			acc = hapB << 16;
+			k_pairLo = (uint32_t)pair; k_pairHi = (uint32_t)(pair >> 32);
+			k_fstartLo = (uint32_t)fstart; k_fstartHi = (uint32_t)((uint64_t)fstart >> 32);
+			k_flen = (uint32_t)flen | (seReverse ? 0x80000000u : 0u);
+			k_posmod = posmod; k_frag = fragCount;
+			// name_off (17 bits) | name_len << 17 (7 bits) | digits of posmod << 24 | digits of fragCount << 28
+			k_name = (uint32_t)bin.name_off | ((uint32_t)bin.name_len << 17) | ((uint32_t)f_ndigits(posmod) << 24) | ((uint32_t)f_ndigits(fragCount) << 28);
+		}
+
+#pragma unroll 1
+		for (int p = 0; p < count; p++) {
+			w.c0 = __shfl_sync(0xffffffffu, k_pairLo, p); w.c1 = __shfl_sync(0xffffffffu, k_pairHi, p);
+			const uint32_t flenRev = __shfl_sync(0xffffffffu, k_flen, p);
+			const uint32_t posmod = __shfl_sync(0xffffffffu, k_posmod, p), fragCount = __shfl_sync(0xffffffffu, k_frag, p);
+			const uint32_t nameNd = __shfl_sync(0xffffffffu, k_name, p);
+			const bool seReverse = (flenRev >> 31) != 0;
 
 			// ---- prefetch the packed windows of both mates (data words lanes 0..15, mask words lanes 16..24)
 			// (global -> shared without passing through registers; waited for after phase A of the first mate)
 			uint32_t g0lo;                                   // low five bits of the two window origins
 			{
-				const int64_t g0b = fstart + flen - RL;
+				const int64_t fstart = (int64_t)(((uint64_t)__shfl_sync(0xffffffffu, k_fstartHi, p) << 32) | __shfl_sync(0xffffffffu, k_fstartLo, p));
+				const int64_t g0b = fstart + (int)(flenRev & 0x7fffffffu) - RL;
 				const int64_t g0a = seReverse ? g0b : fstart;
 				g0lo = ((uint32_t)g0a & 31u) | (((uint32_t)g0b & 31u) << 8);
 				if (lane < 25) {
@@ -693,13 +765,12 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 			// ---- header digits: lanes 0..9 digit d of posmod, lanes 10..19 digit d of fragCount
 			const uint32_t dsrc = lane < 10 ? posmod : fragCount;
-			const uint4 dc = s_dig[lane];                                            // {10^d, M, S, d == 0}
-			const uint32_t geMask = __ballot_sync(0xffffffffu, dsrc >= dc.x);
-			const int nd1 = 1 + __popc(geMask & 0x3feu), nd2 = 1 + __popc(geMask & 0xff800u);
+			const uint4 dc = s_dig[lane];                                            // {10^d (unused here), M, S, d == 0}
+			const int nd1 = (int)((nameNd >> 24) & 15u), nd2 = (int)(nameNd >> 28);
 			uint32_t qd = __umulhi(dsrc, dc.y) >> dc.z;
 			if (dc.w) qd = dsrc;
 			const uint32_t dg = qd - 10u * (__umulhi(qd, 0xCCCCCCCDu) >> 3) + '0';
-			const int nameLen = bin.name_len;
+			const int nameLen = (int)((nameNd >> 17) & 127u), nameOff = (int)(nameNd & 0x1ffffu);
 			const int H = nameLen + nd1 + 1 + nd2 + (t.paired ? 2 : 0) + 1;
 			const int hWords = (H + 31) >> 5;
 #pragma unroll
@@ -708,7 +779,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				const int i = lane + 32 * r;
 				uint32_t ch = '\n';
 				int srcLane = 0;
-				if (i < nameLen) ch = (uint8_t)P.names[bin.name_off + i];
+				if (i < nameLen) ch = (uint8_t)P.names[nameOff + i];
 				else {
 					const int k = i - nameLen;
 					if (k < nd1) { srcLane = nd1 - 1 - k; ch = 0; }
@@ -827,10 +898,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			}
 		}
 		{
-			const uint32_t ticket = (slotEnd - 1u) / FG_CHUNK, blobBase = ticket * (FG_CHUNK * FG_SLOT);
+			const uint32_t ticket = (uint32_t)chunk, blobBase = ticket * (FG_CHUNK * FG_SLOT);
 			if (lane == 0) {
 				P.tileState[ticket] = ((unsigned long long)(pos1 - blobBase) << 31) | (pos2 - blobBase);   // blob lengths, scanned by pass 2
-				const uint32_t nPairs = slotEnd - ticket * FG_CHUNK;
+				const uint32_t nPairs = (uint32_t)count;
 				atomicAdd(&P.result->bases, (unsigned long long)(acc & 0xffffu)); atomicAdd(&P.result->hapBytes, (unsigned long long)(acc >> 16));
 				atomicAdd(&P.result->pairs, (unsigned long long)nPairs); atomicAdd(&P.result->reads, (unsigned long long)(nPairs * nMates));
 			}
