@@ -60,8 +60,8 @@ struct ssc_handle {
 	int device = 0;
 	int smCount = 0;
 	int smemLimit = 0;
-	cudaStream_t compute = nullptr, copy = nullptr;
-	cudaEvent_t evStart = nullptr, evStop = nullptr, evGen[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
+	cudaStream_t compute = nullptr, copy = nullptr, copy2 = nullptr;   // copy/copy2: device->host of file 1 / file 2 (two copy engines)
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evGen[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr}, evCopy2[2] = {nullptr, nullptr};
 
 	// options
 	int64_t batchPairs = 1 << 20;
@@ -270,11 +270,13 @@ int ssc_create(int device, ssc_handle** out) {
 	h->smemLimit = (int)prop.sharedMemPerBlockOptin - 1024;
 	CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->copy2, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&h->evStart));
 	CK(cudaEventCreate(&h->evStop));
 	for (int i = 0; i < 2; i++) {
 		CK(cudaEventCreateWithFlags(&h->evGen[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evCopy[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evCopy2[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evStage[i], cudaEventDisableTiming));
 		CK(cudaMalloc((void**)&h->d_result[i], sizeof(ssc::BatchResult)));
 		CK(cudaMallocHost((void**)&h->h_result[i], sizeof(ssc::BatchResult)));
@@ -300,6 +302,7 @@ int ssc_destroy(ssc_handle* h) {
 		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();
 		if (h->evGen[b]) cudaEventDestroy(h->evGen[b]);
 		if (h->evCopy[b]) cudaEventDestroy(h->evCopy[b]);
+		if (h->evCopy2[b]) cudaEventDestroy(h->evCopy2[b]);
 		if (h->evStage[b]) cudaEventDestroy(h->evStage[b]);
 	}
 	h->d_isizeT.release(); h->d_insT.release(); h->d_delT.release(); h->d_qualT.release();
@@ -316,6 +319,7 @@ int ssc_destroy(ssc_handle* h) {
 	if (h->evStop) cudaEventDestroy(h->evStop);
 	if (h->compute) cudaStreamDestroy(h->compute);
 	if (h->copy) cudaStreamDestroy(h->copy);
+	if (h->copy2) cudaStreamDestroy(h->copy2);
 	delete h;
 	return SSC_OK;
 }
@@ -626,13 +630,15 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 		rc = check_result(h, res[buf]);
 		if (rc) { cudaDeviceSynchronize(); return rc; }
 		CK(cudaMemcpyAsync(h->h_out[buf][0], h->d_out[buf][0], res[buf].bytes1, cudaMemcpyDeviceToHost, h->copy));
-		if (nFiles == 2) CK(cudaMemcpyAsync(h->h_out[buf][1], h->d_out[buf][1], res[buf].bytes2, cudaMemcpyDeviceToHost, h->copy));
+		if (nFiles == 2) CK(cudaMemcpyAsync(h->h_out[buf][1], h->d_out[buf][1], res[buf].bytes2, cudaMemcpyDeviceToHost, h->copy2));
 		CK(cudaEventRecord(h->evCopy[buf], h->copy));
+		CK(cudaEventRecord(h->evCopy2[buf], h->copy2));
 		h->stats.d2h_bytes += res[buf].bytes1 + res[buf].bytes2;
 		if (k >= 1) {
 			// sink batch k-1 (its copy was issued in the previous iteration)
 			const int pb = (k - 1) & 1;
 			CK(cudaEventSynchronize(h->evCopy[pb]));
+			CK(cudaEventSynchronize(h->evCopy2[pb]));
 			if (k + 1 < nb) {
 				// device slab pb is free again: launch batch k+1 into it before the host-side sink work
 				rc = launch_batch(h, pb, batches[k + 1].lo, batches[k + 1].hi);
@@ -651,6 +657,7 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 	{
 		const int pb = (nb - 1) & 1;
 		CK(cudaEventSynchronize(h->evCopy[pb]));
+		CK(cudaEventSynchronize(h->evCopy2[pb]));
 		int src = sink(user, (const char*)h->h_out[pb][0], res[pb].bytes1, nFiles == 2 ? (const char*)h->h_out[pb][1] : nullptr,
 		               nFiles == 2 ? res[pb].bytes2 : 0, batches[nb - 1].lo, batches[nb - 1].hi - batches[nb - 1].lo);
 		if (src) return fail(SSC_ERR_SINK, "sink returned %d", src);
