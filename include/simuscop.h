@@ -121,6 +121,7 @@ typedef struct ssc_stats {
 	double   gen_kernel_ms;    /* CUDA-event time of the generation kernel alone (ssc_generate_device) */
 	double   compact_kernel_ms;/* CUDA-event time of the compaction kernel alone (ssc_generate_device) */
 	uint64_t timed_batches;    /* launches covered by gen_kernel_ms */
+	uint64_t gz_bytes;         /* gzip mode: compressed bytes written to the slabs (fastq_bytes stays the plain size) */
 } ssc_stats;
 
 /*
@@ -139,7 +140,9 @@ int ssc_create(int device, ssc_handle** out);
 int ssc_destroy(ssc_handle* h);
 
 /* "batch_pairs" (pairs per kernel launch), "fp64_search" (0/1: use the FP64 linear-search
- * ground-truth kernel instead of the integer-threshold kernel). */
+ * ground-truth kernel instead of the integer-threshold kernel), "force_generic" (0/1), "gzip" (0/1: the slabs
+ * handed to the sink hold concatenated gzip members -- a valid .gz stream of the same FASTQ bytes -- compressed on
+ * the GPU; the plain bytes of SeqWriter::write are the default). */
 int ssc_set_option(ssc_handle* h, const char* key, int64_t value);
 
 int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t);
@@ -186,6 +189,11 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi,
 int ssc_table_lookup_host(const double* cdf, int n, uint32_t u);
 /* Same for a 4-symbol substitution row encoded as {S0,S1,S2,base}. */
 int ssc_sub_lookup_host(const double* cdf4, uint32_t u);
+
+/* Host-only diagnostic (no GPU needed): one gzip member of in[0..n) built with the device encoder's own tables
+ * (Huffman code fitted to the byte histogram of `sample`, CRC-32 by the kernel's lane-strided algebra) and bit
+ * packing.  Returns the member size, or -1.  Tests inflate it with zlib. */
+int64_t ssc_gzip_member_host(const uint8_t* in, uint32_t n, const uint8_t* sample, size_t sample_n, uint8_t* out, size_t cap);
 
 int ssc_get_stats(ssc_handle* h, ssc_stats* out);
 int ssc_reset_stats(ssc_handle* h);

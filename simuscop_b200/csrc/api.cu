@@ -15,6 +15,7 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "tables.h"
+#include "gz.h"
 
 namespace {
 
@@ -67,6 +68,11 @@ struct ssc_handle {
 	int64_t batchPairs = 1 << 20;
 	bool fp64 = false;
 	bool forceGeneric = false;
+	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
+	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
+	ssc::GzTables* d_gzTab = nullptr;
+	uint8_t* d_gzBlobs[2] = {nullptr, nullptr};
+	DevBuf<unsigned long long> d_gzLens;
 
 	// profile
 	bool haveProfile = false;
@@ -151,6 +157,7 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 		for (int f = 0; f < 2; f++) { if (h->d_slots[f]) cudaFree(h->d_slots[f]); h->d_slots[f] = nullptr; }
 		h->slabPairs = pairs; h->slabCap = cap;
 		for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_slots[f], (size_t)pairs * FG_SLOT + 64));
+		for (int f = 0; f < 2; f++) { if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]); h->d_gzBlobs[f] = nullptr; }
 		CK(h->d_ticket2.alloc(1));
 		CK(h->d_blobPrefix.alloc((size_t)(pairs / 16) + 2));
 		int nTiles = (int)(pairs / 16) + 2;   // enough for every kernel's tile size
@@ -160,6 +167,11 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 			CK(h->d_tileState[b].alloc(nTiles));
 			CK(h->d_ticket[b].alloc(1));
 		}
+	}
+	if (h->gzip && !h->d_gzBlobs[0]) {
+		for (int f = 0; f < 2; f++) CK(cudaMalloc((void**)&h->d_gzBlobs[f], (size_t)h->slabPairs * FG_SLOT + 64));
+		CK(h->d_gzLens.alloc((size_t)(h->slabPairs / 16) + 2));
+		if (!h->d_gzTab) CK(cudaMalloc((void**)&h->d_gzTab, sizeof(ssc::GzTables)));
 	}
 	if (needHost)
 		for (int b = 0; b < 2; b++)
@@ -176,6 +188,32 @@ int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
 	size_t b = std::upper_bound(pb.begin(), pb.end(), p) - pb.begin() - 1;   // pb[b] <= p < pb[b+1]
 	int64_t emitCount = h->emitBaseAll[b + 1] - h->emitBaseAll[b];
 	return h->emitBaseAll[b] + std::min<int64_t>(p - pb[b], emitCount);
+}
+
+// Fits the gzip Huffman table of a plan to the first tickets of its first batch (the blobs are in scratch already).
+int build_gz_tables(ssc_handle* h, const ssc::GenParams& P, int nTiles) {
+	const int sample = std::min(nTiles, 256);
+	const size_t pitch = (size_t)FG_CHUNK * FG_SLOT;
+	std::vector<unsigned long long> lens((size_t)sample);
+	std::vector<uint8_t> blob((size_t)sample * pitch);
+	uint64_t hist[256];
+	memset(hist, 0, sizeof(hist));
+	CK(cudaStreamSynchronize(h->compute));
+	CK(cudaMemcpy(lens.data(), P.tileState, lens.size() * 8, cudaMemcpyDeviceToHost));
+	for (int f = 0; f < (h->dt.paired ? 2 : 1); f++) {
+		CK(cudaMemcpy(blob.data(), f ? P.out2 : P.out1, blob.size(), cudaMemcpyDeviceToHost));
+		for (int j = 0; j < sample; j++) {
+			const size_t n = f ? (size_t)(lens[j] & 0x7fffffffull) : (size_t)(lens[j] >> 31);
+			const uint8_t* p = blob.data() + (size_t)j * pitch;
+			for (size_t i = 0; i < n; i++) hist[p[i]]++;
+		}
+	}
+	ssc::GzTables tab;
+	const char* err = ssc::gz_build_tables(hist, &tab);
+	if (err[0]) return fail(SSC_ERR_INVALID, "gzip tables: %s", err);
+	CK(cudaMemcpy(h->d_gzTab, &tab, sizeof(tab), cudaMemcpyHostToDevice));
+	h->haveGz = true;
+	return SSC_OK;
 }
 
 int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
@@ -219,9 +257,24 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			e0 = h->kev[h->kevUsed]; e1 = h->kev[h->kevUsed + 1]; e2 = h->kev[h->kevUsed + 2];
 			h->kevUsed += 3;
 		}
-		CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, e2));
-		h->stats.launches += 2;
+		if (!h->gzip) {
+			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, e2, true));
+			h->stats.launches += 2;
+		} else {
+			// gzip mode: blobs -> (first batch of a plan: fit the Huffman table to a sample) -> one gzip member per blob -> pass 2 on the members
+			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, nullptr, false));
+			if (!h->haveGz) { int rc = build_gz_tables(h, P, nTiles); if (rc) return rc; }
+			CK(cudaMemsetAsync(h->d_gzLens.p, 0, sizeof(unsigned long long) * nTiles, s));
+			CK(ssc::launch_deflate_blobs(P.out1, P.out2, P.tileState, nTiles, FG_CHUNK * FG_SLOT, h->d_gzBlobs[0], h->d_gzBlobs[1], h->d_gzLens.p,
+			                             FG_CHUNK * FG_SLOT, h->d_gzTab, &P.result->errorFlags, h->smCount, s));
+			ssc::GenParams P2 = P;
+			P2.out1 = h->d_gzBlobs[0]; P2.out2 = h->d_gzBlobs[1]; P2.tileState = h->d_gzLens.p;
+			CK(ssc::launch_pass2(P2, h->smCount, s));
+			if (e2) CK(cudaEventRecord(e2, s));
+			h->stats.launches += 3;
+		}
 	} else {
+		if (h->gzip) return fail(SSC_ERR_INVALID, "gzip output needs the fast kernel (kmer 3, read length 33..160)");
 		ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
 		if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
 		CK(ssc::launch_generate(P, v, grid, s));
@@ -236,10 +289,12 @@ int check_result(ssc_handle* h, const ssc::BatchResult& r) {
 	if (r.errorFlags & 1u) return fail(SSC_ERR_OVERFLOW, "output slab overflow (internal capacity estimate too small)");
 	if (r.errorFlags & 2u) return fail(SSC_ERR_OVERFLOW, "a read outgrew the per-read scratch (insertions > 96 bases)");
 	if (r.errorFlags & 4u) return fail(SSC_ERR_OVERFLOW, "more than 32 indel events or 128 inserted bases in one read");
+	if (r.errorFlags & 8u) return fail(SSC_ERR_OVERFLOW, "a gzip member outgrew its scratch blob");
 	h->stats.pairs_emitted += r.pairs;
 	h->stats.reads_emitted += r.reads;
 	h->stats.bases_emitted += r.bases;
-	h->stats.fastq_bytes += r.bytes1 + r.bytes2;
+	h->stats.fastq_bytes += h->gzip ? r.rawBytes : r.bytes1 + r.bytes2;
+	if (h->gzip) h->stats.gz_bytes += r.bytes1 + r.bytes2;
 	h->stats.hap_bytes += r.hapBytes;
 	return SSC_OK;
 }
@@ -311,7 +366,9 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
 	h->d_hap2.release(); h->d_hapN.release();
-	h->d_ticket2.release(); h->d_blobPrefix.release();
+	h->d_ticket2.release(); h->d_blobPrefix.release(); h->d_gzLens.release();
+	for (int f = 0; f < 2; f++) if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]);
+	if (h->d_gzTab) cudaFree(h->d_gzTab);
 	h->d_cenStarts.release(); h->d_cenLens.release(); h->d_cenGc.release(); h->d_cenNn.release();
 	h->d_bins.release(); h->d_emitBase.release(); h->d_risky.release(); h->d_names.release();
 	for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
@@ -331,6 +388,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 		h->batchPairs = value;
 		return SSC_OK;
 	}
+	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
 	if (!strcmp(key, "fp64_search")) {
 		if (h->havePlan) return fail(SSC_ERR_STATE, "fp64_search must be set before ssc_set_plan");
@@ -394,6 +452,7 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	d.delThresh = t->del_rate / one_minus;
 	h->haveProfile = true;
 	h->havePlan = false;
+	h->haveGz = false;
 	return SSC_OK;
 }
 
@@ -489,6 +548,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	const bool paired = t.paired != 0;
 	h->seed = seed;
 	h->havePlan = false;
+	h->haveGz = false;
 
 	// ---- validate, planned pairs, risky bins
 	std::vector<int64_t>& pb = h->planBaseAll;
@@ -730,6 +790,17 @@ int ssc_sub_lookup_host(const double* cdf4, uint32_t u) {
 	if (!cdf4) return -1;
 	ssc::SubRow r = ssc::make_sub_row(cdf4);
 	return (int)(r.base + (u > r.s0) + (u > r.s1) + (u > r.s2));
+}
+
+int64_t ssc_gzip_member_host(const uint8_t* in, uint32_t n, const uint8_t* sample, size_t sample_n, uint8_t* out, size_t cap) {
+	if (!in || !out || n < 4) return -1;
+	uint64_t hist[256];
+	memset(hist, 0, sizeof(hist));
+	for (size_t i = 0; i < sample_n; i++) hist[sample[i]]++;
+	ssc::GzTables tab;
+	const char* err = ssc::gz_build_tables(hist, &tab);
+	if (err[0]) { fail(SSC_ERR_INVALID, "gzip tables: %s", err); return -1; }
+	return (int64_t)ssc::gz_member_host(&tab, in, n, out, cap);
 }
 
 int ssc_get_stats(ssc_handle* h, ssc_stats* out) {

@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				const uint32_t nPairs = (uint32_t)count;
 				atomicAdd(&P.result->bases, (unsigned long long)(acc & 0xffffu)); atomicAdd(&P.result->hapBytes, (unsigned long long)(acc >> 16));
 				atomicAdd(&P.result->pairs, (unsigned long long)nPairs); atomicAdd(&P.result->reads, (unsigned long long)(nPairs * nMates));
+				atomicAdd(&P.result->rawBytes, (unsigned long long)(pos1 - blobBase) + (pos2 - blobBase));
 			}
 		}
 	}
@@ -935,7 +936,7 @@ static cudaError_t launch_fast_variant(const GenParams& P, size_t smemBytes, int
 
 // P.out1/out2 = blob scratch, P.dense1/dense2 = final slabs, P.nTiles = tickets of FG_CHUNK pairs
 cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
-                                 cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
+                                 cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool pass2) {
 	const int nch = (P.t.RL + 31) / 32;   // the kernel's chunk count is exact: only the last chunk has idle lanes
 	cudaError_t e;
 	if (e0) cudaEventRecord(e0, stream);
@@ -957,11 +958,18 @@ cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes
 	}
 	if (e != cudaSuccess) return e;
 	if (e1) cudaEventRecord(e1, stream);
+	if (!pass2) return cudaSuccess;
+	e = launch_pass2(P, smCount, stream);
+	if (e2) cudaEventRecord(e2, stream);
+	return e;
+}
+
+// pass 2: blobs P.out1/out2 with packed lengths P.tileState -> dense slabs P.dense1/dense2, totals in P.result->bytes1/2
+cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream) {
 	scan_blobs_kernel<<<1, SC_THREADS, 0, stream>>>(P);
 	int cgrid = smCount * 8;
 	if (cgrid * (CP_THREADS / 32) > P.nTiles) cgrid = (P.nTiles + CP_THREADS / 32 - 1) / (CP_THREADS / 32);
 	move_blobs_kernel<<<cgrid, CP_THREADS, 0, stream>>>(P);
-	if (e2) cudaEventRecord(e2, stream);
 	return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
            "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
-           "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host"]
+           "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host"]
 
 _lib = None
 
@@ -43,6 +43,8 @@ def lib():
         L.ssc_reset_stats.argtypes = [C.c_void_p]
         L.ssc_table_lookup_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         L.ssc_sub_lookup_host.argtypes = [C.c_void_p, C.c_uint32]
+        L.ssc_gzip_member_host.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ssc_gzip_member_host.restype = C.c_int64
         _lib = L
     return _lib
 

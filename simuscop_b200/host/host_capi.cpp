@@ -92,13 +92,18 @@ int ssh_run(ssh_job* job, int device) {
 	}
 	const char* dumpPrefix = getenv("SIMUSCOP_DUMP_PLAN");
 	if (const char* bp = getenv("SIMUSCOP_BATCH_PAIRS")) for (auto* d : devs) ssc_set_option(d, "batch_pairs", atoll(bp));
+	// SIMUSCOP_GZIP=1: the same FASTQ, compressed on the GPU, written as <name>.fq.gz (concatenated gzip members)
+	const char* gzEnv = getenv("SIMUSCOP_GZIP");
+	const bool gz = gzEnv && atoi(gzEnv) != 0;
+	if (gz) for (auto* d : devs) ssc_set_option(d, "gzip", 1);
 	sschost::Job& J = job->job;
 	const int G = (int)devs.size();
 	for (int s = 0; s < (int)J.samples.size() && !rc; s++) {
 		const std::string prefix = J.cfg.str["output"] + "/" + J.samples[s].stem;
 		const bool paired = J.cfg.paired();
-		const std::string f1 = paired ? prefix + "_1.fq" : prefix + ".fq";
-		const std::string f2 = paired ? prefix + "_2.fq" : "";
+		const std::string ext = gz ? ".fq.gz" : ".fq";
+		const std::string f1 = paired ? prefix + "_1" + ext : prefix + ext;
+		const std::string f2 = paired ? prefix + "_2" + ext : "";
 		std::string dump;
 		if (dumpPrefix) dump = std::string(dumpPrefix) + "." + std::to_string(s) + ".plan";
 		int64_t planned = 0, emitted = 0;

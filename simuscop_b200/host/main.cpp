@@ -1,7 +1,7 @@
 // main.cpp -- drop-in `simuReads <configuration file>` (reference src/simuReads.cpp:24-97).
 // New knobs come from the environment only, so existing configuration files stay valid:
 //   SIMUSCOP_SEED (default: wall clock, like the reference), SIMUSCOP_DEVICE (default 0),
-//   SIMUSCOP_DUMP_PLAN=<prefix>, SIMUSCOP_BATCH_PAIRS.
+//   SIMUSCOP_DUMP_PLAN=<prefix>, SIMUSCOP_BATCH_PAIRS, SIMUSCOP_GZIP=1 (<name>.fq.gz, compressed on the GPU).
 #include <chrono>
 #include <cstdlib>
 #include <ctime>

@@ -240,3 +240,57 @@ def test_device_plan_equals_host_plan(built, workdir):
         assert len(dumps["host"]) == len(dumps["dev"])
         for a, b in zip(dumps["host"], dumps["dev"]):
             assert a == b
+
+
+@pytest.mark.parametrize("name,batch", [("pe_xten", 0), ("pe_xten", 4096), ("se_ploidy1", 0), ("pe_tiny", 0)])
+def test_gzip_output_inflates_to_the_plain_fastq(name, batch, built, workdir):
+    """ssc_set_option("gzip", 1): the slabs are concatenated gzip members compressed on the GPU (one per 32-record
+    blob, literal-only dynamic Huffman blocks, CRC-32 + ISIZE trailers checked by zlib); inflated they are byte for
+    byte the plain output, which is the instrumented reference's."""
+    import gzip
+    from simuscop_b200 import cuda_binding
+    scn = helpers.build_scenario(name, workdir)
+    plans, out = helpers.run_reference_philox(scn, tag="gz")
+    plan = planfile.read_plan(plans[0])
+    r1p, r2p = helpers.sample_files(out, plan, 0, scn)
+    r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
+    g = cuda_binding.Generator(0)
+    try:
+        g.set_option("gzip", 1)
+        if batch:
+            g.set_option("batch_pairs", batch)
+        g.load_plan(plan, scn["seed"])
+        z1, z2 = g.generate()
+        st = g.stats()
+        assert gzip.decompress(z1) == r1
+        assert (gzip.decompress(z2) if z2 else b"") == r2
+        assert st["fastq_bytes"] == len(r1) + len(r2) and st["gz_bytes"] == len(z1) + len(z2)
+        assert len(z1) < 0.6 * len(r1)          # ~0.3 with XTen's 7 quality symbols, ~0.5 with 40
+        # back to plain output on the same handle
+        g.set_option("gzip", 0)
+        f1, f2 = g.generate()
+        assert f1 == r1 and f2 == r2
+    finally:
+        g.close()
+
+
+def test_cli_gzip_files(built, workdir):
+    """SIMUSCOP_GZIP=1: <name>_1.fq.gz / _2.fq.gz inflate to the files of the plain run."""
+    import gzip
+    import os
+    import subprocess
+    from simuscop_b200 import paths, synth
+    scn = helpers.build_scenario("pe_xten", workdir)
+    d = scn["dir"]
+    outs = {}
+    for tag, env in (("plain", {}), ("gz", {"SIMUSCOP_GZIP": "1"})):
+        out = os.path.join(d, "out_clig_" + tag)
+        cfg = os.path.join(d, "cfg_clig_%s.txt" % tag)
+        synth.write_config(cfg, output=out, **scn["kw"])
+        r = subprocess.run([paths.SIMUREADS, cfg], env=dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), **env), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = out
+    assert sorted(os.listdir(outs["gz"])) == ["test_1.fq.gz", "test_2.fq.gz"]
+    for k in ("1", "2"):
+        assert gzip.decompress(helpers.read_file(os.path.join(outs["gz"], "test_%s.fq.gz" % k))) == \
+            helpers.read_file(os.path.join(outs["plain"], "test_%s.fq" % k))

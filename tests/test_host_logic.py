@@ -169,3 +169,36 @@ def test_two_rank_sharding_concatenates_to_single_rank_output(built, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert open(flag).read() == "ok 2"
+
+
+def test_gzip_member_host_mirror_inflates(built):
+    """The device gzip encoder's tables and algebra on the host (ssc_gzip_member_host: Huffman code fitted to a sample,
+    dynamic block header, bit packing, lane-strided CRC-32 combination): zlib must accept every member."""
+    import ctypes as C
+    import gzip
+    import random
+    L = cuda_binding.lib()
+    rnd = random.Random(7)
+
+    def fastq(n):
+        rec = []
+        for i in range(n):
+            ln = rnd.choice([151, 150, 149, 152, 96])
+            rec.append("@test#chr%d#%d#%d/1\n%s\n+\n%s\n" % (rnd.randint(1, 22), rnd.randint(0, 999999), i + 1,
+                       "".join(rnd.choice("ACGT") for _ in range(ln)), "".join(rnd.choice("FFFFFFF:A<,#") for _ in range(ln))))
+        return "".join(rec).encode()
+    sample = fastq(100)
+    members = []
+    for n, cut in ((1, 0), (2, 1), (32, 2), (33, 3), (64, 0)):
+        d = fastq(n)
+        d = d[:len(d) - cut] if cut else d
+        buf = C.create_string_buffer(2 * len(d) + 1024)
+        m = L.ssc_gzip_member_host(d, len(d), sample, len(sample), buf, len(buf))
+        assert m > 0
+        assert gzip.decompress(buf.raw[:m]) == d
+        members.append((d, buf.raw[:m]))
+    assert gzip.decompress(b"".join(z for _, z in members)) == b"".join(d for d, _ in members)
+    noise = bytes(rnd.randrange(256) for _ in range(4099))          # every byte value stays encodable
+    buf = C.create_string_buffer(4 * len(noise))
+    m = L.ssc_gzip_member_host(noise, len(noise), sample, len(sample), buf, len(buf))
+    assert gzip.decompress(buf.raw[:m]) == noise
