@@ -33,10 +33,6 @@
 #include "kernels.h"
 #include "philox.cuh"
 
-#ifndef SSC_SLOW_UNROLL
-#define SSC_SLOW_UNROLL 0
-#endif
-
 namespace ssc {
 
 #define ST_A (1ull << 62)
@@ -167,19 +163,7 @@ __device__ __forceinline__ long long f_draw_pos(uint32_t u, int spos, int epos) 
 	return (long long)v;
 }
 
-// warp-cooperative lookup in a compressed CDF held in shared memory (n <= 1024): sym[#{i : T[i] < u}]
-__device__ __forceinline__ int coop_lookup(const uint32_t* T, const uint16_t* sym, int n, uint32_t u, int lane) {
-	const int stride = (n + 31) >> 5;
-	int i1 = (lane + 1) * stride - 1;
-	if (i1 > n - 1) i1 = n - 1;
-	const int blk = __popc(__ballot_sync(0xffffffffu, T[i1] < u && (lane + 1) * stride <= n));
-	const int i2 = blk * stride + lane;
-	const bool v2 = lane < stride && i2 < n && T[i2] < u;
-	const int cnt = blk * stride + __popc(__ballot_sync(0xffffffffu, v2));
-	return (int)sym[cnt < n ? cnt : n - 1];
-}
-
-// uniform binary search (all lanes the same u), small tables
+// binary search in a compressed CDF held in shared memory: sym[#{i : T[i] < u}] (per lane or warp-uniform u)
 __device__ __forceinline__ int uni_lookup(const uint32_t* T, const uint16_t* sym, int n, uint32_t u) {
 	int lo = 0, len = n - 1;
 	while (len > 0) {
@@ -256,26 +240,6 @@ __device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur,
 	int k = 0;
 	for (int s = q.pitch >> 1; s > 0; s >>= 1) if (qt[k + s - 1] < u3) k += s;
 	return q.gSym[qrow * q.pitch + k];
-}
-
-// substitution + quality for one output base of the slow path; returns (char | qual << 8)
-template <int QP>
-__device__ __forceinline__ uint32_t call_base(const WarpCtx& w, uint32_t cur, int row, bool bad, bool curN, int binIdx,
-                                              uint32_t u2, uint32_t u3) {
-	int call;
-	if (bad) call = curN ? -1 : (int)cur;
-	else {
-		const uint4 s = w.sub[row * w.subPitch + binIdx];
-		// word 3 = qualBaseS + ref * 4 * F_QROW + base * F_QROW (ref = cur on this branch); F_QROW in [64, 85) => >> 6 is / F_QROW for base <= 3
-		call = (int)((s.w - w.qualBaseS - cur * (4u * F_QROW)) >> 6) + (u2 > s.x) + (u2 > s.y) + (u2 > s.z);
-	}
-	uint32_t ch, q;
-	if (call < 0) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }    // randomInteger(33, 53), Profile.cpp:1583
-	else {
-		ch = __byte_perm(w.baseChars, 0, 0x4440 | call);
-		q = qual_lookup<QP>(w.q, cur, (uint32_t)call, (uint32_t)binIdx, w.B, u3);
-	}
-	return ch | (q << 8);
 }
 
 // template base code (0..3, 4 = non-ACGT) of read position j, from the shared window
@@ -418,22 +382,6 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 		stage[H + j] = (uint8_t)ch;
 		stage[H + m + 3 + j] = (uint8_t)q;
 	};
-#if SSC_SLOW_UNROLL
-	// the draws of the first NCH chunks are the caller's registers
-#pragma unroll
-	for (int c = 0; c < NCH; c++) {
-		const int j = c * 32 + lane;
-		if (j < m) emit(j, x2[c], x3[c]);
-	}
-#pragma unroll 1
-	for (int c = NCH; c < chunksM; c++) {
-		const int j = c * 32 + lane;
-		if (j < m) {
-			const u32x4 blk = philox_rk(w.c0, w.c1, c2cyc, (uint32_t)j, w.rk);
-			emit(j, blk.z, blk.w);
-		}
-	}
-#else
 	// the draws of the first NCH chunks are the caller's registers; select by chunk without dynamic indexing
 	// (kept rolled: the hot loop has to stay inside the instruction cache)
 #pragma unroll 1
@@ -449,7 +397,6 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 		}
 		if (j < m) emit(j, u2, u3);
 	}
-#endif
 	return m;
 }
 

@@ -20,6 +20,8 @@ plan = planfile.read_plan(plans[0])
 plan.bins["read_count"] *= scale
 g = cuda_binding.Generator(0)
 g.set_option("batch_pairs", int(os.environ.get("QB_BATCH", 1 << 21)))
+if os.environ.get("QB_GZIP"):
+    g.set_option("gzip", 1)
 t = time.time()
 g.load_plan(plan, 7)
 print("load_plan %.2fs planned=%d emitted=%d" % (time.time() - t, g.planned, g.emitted))
