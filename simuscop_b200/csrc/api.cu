@@ -68,6 +68,7 @@ struct ssc_handle {
 	int64_t batchPairs = 1 << 20;
 	bool fp64 = false;
 	bool forceGeneric = false;
+	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
 	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
 	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
 	ssc::GzTables* d_gzTab = nullptr;
@@ -248,6 +249,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	int grid = std::min(nTiles, h->smCount);
 	if (fast) {
 		grid = std::min((nTiles + FG_GEN - 1) / FG_GEN, h->smCount);
+		if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
 		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
@@ -389,6 +391,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 		return SSC_OK;
 	}
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
+	if (!strcmp(key, "max_ctas")) { if (value < 0) return fail(SSC_ERR_INVALID, "max_ctas must be >= 0"); h->maxCtas = (int)value; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
 	if (!strcmp(key, "fp64_search")) {
 		if (h->havePlan) return fail(SSC_ERR_STATE, "fp64_search must be set before ssc_set_plan");

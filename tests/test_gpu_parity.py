@@ -294,3 +294,29 @@ def test_cli_gzip_files(built, workdir):
     for k in ("1", "2"):
         assert gzip.decompress(helpers.read_file(os.path.join(outs["gz"], "test_%s.fq.gz" % k))) == \
             helpers.read_file(os.path.join(outs["plain"], "test_%s.fq" % k))
+
+
+@pytest.mark.parametrize("ctas", [1, 3])
+def test_many_tickets_per_warp(ctas, built, workdir):
+    """At full size a warp of the generation kernel works through a dozen tickets of 32 pairs one after the other; the
+    parity scenarios are small enough for one ticket per warp.  Capping the grid makes every warp take many tickets
+    (shared-memory windows, headers and indel scratch are reused across pairs and tickets) -- same bytes, plain and gzip."""
+    import gzip
+    from simuscop_b200 import cuda_binding
+    for name in ("pe_xten", "pe_variants"):
+        scn = helpers.build_scenario(name, workdir)
+        plans, out = helpers.run_reference_philox(scn, tag="mt")
+        plan = planfile.read_plan(plans[0])
+        r1p, r2p = helpers.sample_files(out, plan, 0, scn)
+        r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
+        g = cuda_binding.Generator(0)
+        try:
+            g.set_option("max_ctas", ctas)
+            g.load_plan(plan, scn["seed"])
+            f1, f2 = g.generate()
+            assert helpers.first_diff(f1, r1) == -1 and helpers.first_diff(f2, r2) == -1
+            g.set_option("gzip", 1)
+            z1, z2 = g.generate()
+            assert gzip.decompress(z1) == r1 and gzip.decompress(z2) == r2
+        finally:
+            g.close()
