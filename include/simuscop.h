@@ -156,6 +156,18 @@ int ssc_genome_reserve(ssc_handle* h, uint64_t total_bases);
 int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* first_base);
 int ssc_genome_size(ssc_handle* h, uint64_t* n_bases);
 
+/* Reference-relative construction of haplotype strings on the device (the copy-and-substitute part of
+ * Segment::generateSegSequences, lib/segment/Segment.cpp:124-311: a haplotype of a segment without indel variants is
+ * the reference slice repeated once per copy, with SNP / SNV alleles poked in).  The chromosome is uploaded once
+ * (ssc_reference_upload, any case, ASCII); ssc_genome_append_ref appends `reps` copies of reference bases
+ * [ref_off, ref_off+len) to the store exactly as ssc_genome_append would append that string; ssc_genome_poke then
+ * overwrites single bases (store indices, distinct) with the given characters.  ssc_genome_read decodes store bases
+ * back to upper-case ASCII (non-ACGT -> 'N'), a diagnostic for tests. */
+int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n);
+int ssc_genome_append_ref(ssc_handle* h, uint64_t ref_off, uint64_t len, int32_t reps, uint64_t* first_base);
+int ssc_genome_poke(ssc_handle* h, const int64_t* store_pos, const char* chars, int64_t n);
+int ssc_genome_read(ssc_handle* h, uint64_t start, uint64_t n, char* out);
+
 /* GC census of haplotype-store intervals: the device half of the GC-weighted read plan
  * (Segment::getWeightedLength, lib/segment/Segment.cpp:567-624, which calls calculateGCPercent,
  * lib/mydefine/MyDefine.cpp:279-303, once per 1 kb window / capture target).  For interval i =

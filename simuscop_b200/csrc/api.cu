@@ -90,6 +90,8 @@ struct ssc_handle {
 	// genome
 	DevBuf<uint32_t> d_hap2, d_hapN;
 	uint64_t genomeCap = 0, genomeSize = 0;
+	DevBuf<uint8_t> d_ref;                        // ASCII chromosome for ssc_genome_append_ref
+	uint64_t refSize = 0;
 	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
 	uint8_t* d_stage[2] = {nullptr, nullptr};
 	cudaEvent_t evStage[2] = {nullptr, nullptr};
@@ -367,7 +369,7 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_isizeSym.release(); h->d_insSym.release(); h->d_delSym.release(); h->d_qualSym.release();
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
-	h->d_hap2.release(); h->d_hapN.release();
+	h->d_hap2.release(); h->d_hapN.release(); h->d_ref.release();
 	h->d_ticket2.release(); h->d_blobPrefix.release(); h->d_gzLens.release();
 	for (int f = 0; f < 2; f++) if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]);
 	if (h->d_gzTab) cudaFree(h->d_gzTab);
@@ -498,6 +500,63 @@ int ssc_genome_append(ssc_handle* h, const char* ascii, uint64_t n, uint64_t* fi
 		k ^= 1;
 	}
 	h->genomeSize += n;
+	return SSC_OK;
+}
+
+int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n) {
+	if (!h || (!ascii && n)) return fail(SSC_ERR_INVALID, "null argument");
+	CK(cudaSetDevice(h->device));
+	if (h->d_ref.n < n) CK(h->d_ref.alloc((size_t)n + (size_t)n / 8 + 4096));
+	CK(cudaStreamSynchronize(h->compute));          // earlier ssc_genome_append_ref launches still read the old reference
+	if (n) CK(cudaMemcpy(h->d_ref.p, ascii, (size_t)n, cudaMemcpyHostToDevice));
+	h->refSize = n;
+	h->stats.h2d_bytes += n;
+	return SSC_OK;
+}
+
+int ssc_genome_append_ref(ssc_handle* h, uint64_t ref_off, uint64_t len, int32_t reps, uint64_t* first_base) {
+	if (!h || reps < 0) return fail(SSC_ERR_INVALID, "bad argument");
+	if (ref_off + len > h->refSize) return fail(SSC_ERR_INVALID, "reference range outside the uploaded chromosome");
+	if (h->genomeSize + len * (uint64_t)reps > h->genomeCap) return fail(SSC_ERR_INVALID, "genome append exceeds the reserved %llu bases", (unsigned long long)h->genomeCap);
+	CK(cudaSetDevice(h->device));
+	if (first_base) *first_base = h->genomeSize;
+	for (int32_t r = 0; r < reps && len; r++) {
+		CK(ssc::launch_pack(h->d_ref.p + ref_off, len, SSC_GPAD + h->genomeSize, h->d_hap2.p, h->d_hapN.p, h->d_lut.p, h->compute));
+		h->genomeSize += len;
+		h->stats.launches += 1;
+	}
+	return SSC_OK;
+}
+
+int ssc_genome_poke(ssc_handle* h, const int64_t* store_pos, const char* chars, int64_t n) {
+	if (!h || n < 0 || (n && (!store_pos || !chars))) return fail(SSC_ERR_INVALID, "null argument");
+	if (n == 0) return SSC_OK;
+	CK(cudaSetDevice(h->device));
+	for (int64_t i = 0; i < n; i++)
+		if (store_pos[i] < 0 || (uint64_t)store_pos[i] >= h->genomeSize) return fail(SSC_ERR_INVALID, "poke %lld outside the haplotype store", (long long)i);
+	DevBuf<int64_t> d_pos; DevBuf<uint8_t> d_ch;
+	CK(d_pos.alloc((size_t)n)); CK(d_ch.alloc((size_t)n));
+	CK(cudaMemcpyAsync(d_pos.p, store_pos, (size_t)n * 8, cudaMemcpyHostToDevice, h->compute));
+	CK(cudaMemcpyAsync(d_ch.p, chars, (size_t)n, cudaMemcpyHostToDevice, h->compute));
+	CK(ssc::launch_poke(h->d_hap2.p, h->d_hapN.p, d_pos.p, d_ch.p, n, h->d_lut.p, h->compute));
+	CK(cudaStreamSynchronize(h->compute));
+	d_pos.release(); d_ch.release();
+	h->stats.launches += 1;
+	return SSC_OK;
+}
+
+int ssc_genome_read(ssc_handle* h, uint64_t start, uint64_t n, char* out) {
+	if (!h || (!out && n)) return fail(SSC_ERR_INVALID, "null argument");
+	if (start + n > h->genomeSize) return fail(SSC_ERR_INVALID, "range outside the haplotype store");
+	if (n == 0) return SSC_OK;
+	CK(cudaSetDevice(h->device));
+	DevBuf<uint8_t> d_out;
+	CK(d_out.alloc((size_t)n));
+	CK(ssc::launch_unpack(h->d_hap2.p, h->d_hapN.p, SSC_GPAD + start, n, h->dt.baseChars, d_out.p, h->compute));
+	CK(cudaMemcpyAsync(out, d_out.p, (size_t)n, cudaMemcpyDeviceToHost, h->compute));
+	CK(cudaStreamSynchronize(h->compute));
+	d_out.release();
+	h->stats.launches += 1;
 	return SSC_OK;
 }
 

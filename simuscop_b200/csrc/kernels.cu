@@ -93,6 +93,33 @@ __global__ void pack_kernel(const uint8_t* __restrict__ ascii, uint64_t n, uint6
 }
 
 // ----------------------------------------------------------------------------------------
+// poke_kernel / unpack_kernel: single-base overwrites of the packed store (SNP / SNV alleles on reference-built
+// haplotypes, Segment.cpp:233-311) and the decoder back to ASCII (diagnostic)
+// ----------------------------------------------------------------------------------------
+__global__ void poke_kernel(uint32_t* __restrict__ hap2, uint32_t* __restrict__ hapN, const int64_t* __restrict__ pos,
+                            const uint8_t* __restrict__ chars, int64_t n, const int8_t* __restrict__ lut) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t g = (uint64_t)pos[i] + SSC_GPAD;
+	int code = lut[chars[i]];
+	const uint32_t nbit = 1u << (g & 31);
+	if (code > 3) { atomicOr(&hapN[g >> 5], nbit); code = 0; } else atomicAnd(&hapN[g >> 5], ~nbit);
+	const uint32_t sh = (uint32_t)(g & 15) * 2u;
+	atomicAnd(&hap2[g >> 4], ~(3u << sh));
+	atomicOr(&hap2[g >> 4], (uint32_t)code << sh);
+}
+
+__global__ void unpack_kernel(const uint32_t* __restrict__ hap2, const uint32_t* __restrict__ hapN, uint64_t firstBase, uint64_t n,
+                              uint32_t baseChars, uint8_t* __restrict__ out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t g = firstBase + i;
+	const uint32_t code = (hap2[g >> 4] >> ((g & 15) * 2)) & 3u;
+	const bool isN = (hapN[g >> 5] >> (g & 31)) & 1u;
+	out[i] = isN ? (uint8_t)'N' : (uint8_t)(baseChars >> (8 * code));
+}
+
+// ----------------------------------------------------------------------------------------
 // gc_census_kernel: G/C and non-ACGT base counts of store intervals (one warp per interval),
 // the device half of Segment::getWeightedLength -> calculateGCPercent (Segment.cpp:567-624,
 // MyDefine.cpp:279-303).  A lane takes groups of 32 bases: two data words + one mask word.
@@ -728,6 +755,18 @@ cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, 
 	int blocks = (nBins + threads - 1) / threads;
 	if (fp64) census_kernel<true><<<blocks, threads, 0, stream>>>(t, bins, nBins, seed, riskyAttempt, emitted);
 	else census_kernel<false><<<blocks, threads, 0, stream>>>(t, bins, nBins, seed, riskyAttempt, emitted);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_poke(uint32_t* hap2, uint32_t* hapN, const int64_t* pos, const uint8_t* chars, int64_t n, const int8_t* lut, cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	poke_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hap2, hapN, pos, chars, n, lut);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const uint32_t* hap2, const uint32_t* hapN, uint64_t firstBase, uint64_t n, uint32_t baseChars, uint8_t* out, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hap2, hapN, firstBase, n, baseChars, out);
 	return cudaGetLastError();
 }
 

@@ -42,6 +42,8 @@ cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, ui
                         const int8_t* lut, cudaStream_t stream);
 cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, int nBins, uint64_t seed,
                           uint16_t* riskyAttempt, int32_t* emitted, cudaStream_t stream);
+cudaError_t launch_poke(uint32_t* hap2, uint32_t* hapN, const int64_t* pos, const uint8_t* chars, int64_t n, const int8_t* lut, cudaStream_t stream);
+cudaError_t launch_unpack(const uint32_t* hap2, const uint32_t* hapN, uint64_t firstBase, uint64_t n, uint32_t baseChars, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_gc_census(const uint32_t* hap2, const uint32_t* hapN, const int64_t* starts, const int32_t* lens, int64_t n,
                              uint32_t gcCodes, int32_t* gc, int32_t* nn, cudaStream_t stream);
 cudaError_t launch_locate(const int64_t* emitBase, int64_t nBins, int64_t emitLo, int tilePairs, int nTiles, int32_t* tileStartBin,

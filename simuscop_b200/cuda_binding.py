@@ -11,7 +11,7 @@ from . import abi
 from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
-           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
+           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
            "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host"]
 
 _lib = None
@@ -33,6 +33,10 @@ def lib():
         L.ssc_genome_reserve.argtypes = [C.c_void_p, C.c_uint64]
         L.ssc_genome_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ssc_genome_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ssc_reference_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        L.ssc_genome_append_ref.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+        L.ssc_genome_poke.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
+        L.ssc_genome_read.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.ssc_gc_census.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ssc_set_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -88,6 +92,17 @@ class Generator:
         _ck(lib().ssc_genome_append(self.h, g.ctypes.data, g.size, C.byref(first)))
         assert first.value == 0
         self.set_plan(plan.bins, plan.segs, plan.names, seed)
+
+    def genome_read(self, start, n):
+        """Decode store bases [start, start+n) back to upper-case ASCII (diagnostic)."""
+        buf = C.create_string_buffer(int(n))
+        _ck(lib().ssc_genome_read(self.h, int(start), int(n), buf))
+        return buf.raw[:n]
+
+    def genome_size(self):
+        v = C.c_uint64()
+        _ck(lib().ssc_genome_size(self.h, C.byref(v)))
+        return v.value
 
     def gc_census(self, starts, lens):
         """G/C and non-ACGT base counts of haplotype-store intervals (ssc_gc_census)."""

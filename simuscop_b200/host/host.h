@@ -71,6 +71,7 @@ struct Snp { long long pos; char nucleotide; };
 struct Target { long spos, epos; };
 
 struct Bin { long spos, epos; int hap; double weight; int rc; };
+struct Poke { int hap; long off; char c; };   // substitution at offset off of every copy of the reference slice
 struct BinSpec { long spos, epos; int hap; int kind; long n; long gcStart, gcLen; };   // a bin before its GC draw (host_plan.cpp)
 struct ChrLayout {   // where the haplotype strings of one chromosome live in the device store
 	std::vector<std::vector<int64_t>> base;      // [segment][haplotype] store index of the string, -1 = absent
@@ -116,6 +117,9 @@ public:
 
 	// haplotype strings of one segment (Segment::generateSegSequences, lib/segment/Segment.cpp:124-460)
 	void build_haplotypes(Segment& seg, const std::string& popu, std::vector<std::string>& haps);
+	void phase_segment(Segment& seg);                        // rand()-driven copy-number phasing (Segment.cpp:140-215)
+	bool segment_is_copy_only(const Segment& seg, const std::string& popu);
+	void segment_copies_and_pokes(Segment& seg, const std::string& popu, std::vector<int>& reps, std::vector<Poke>& pokes);
 	// bins + weights (Segment::getWeightedLength, Segment.cpp:550-641)
 	double weighted_length(Segment& seg, const std::string& popu);
 	double weighted_length_from(Segment& seg, const std::vector<std::string>& haps);

@@ -192,8 +192,6 @@ const std::string& Fasta::chromosome(const std::string& chr) {
 	size_t got = fread(&buf[0], 1, raw, f);
 	fclose(f);
 	cached_.assign((size_t)e.length, 'N');
-	static unsigned char up[256];
-	if (!up['a']) for (int i = 0; i < 256; i++) up[i] = (unsigned char)toupper(i);
 	size_t w = 0, i = 0;
 	while (i < got && w < (size_t)e.length) {
 		const char* nlp = (const char*)memchr(buf.data() + i, '\n', got - i);
@@ -201,7 +199,10 @@ const std::string& Fasta::chromosome(const std::string& chr) {
 		size_t n = std::min(lineEnd - i, (size_t)e.length - w);
 		char* dst = &cached_[w];
 		const unsigned char* src = (const unsigned char*)buf.data() + i;
-		for (size_t k = 0; k < n; k++) dst[k] = (char)up[src[k]];
+		for (size_t k = 0; k < n; k++) {                       // toupper without a table: the loop vectorises
+			const unsigned char c = src[k];
+			dst[k] = (char)(c - (unsigned char)(((unsigned char)(c - 'a') < 26u) << 5));
+		}
 		w += n;
 		i = lineEnd + 1;
 	}

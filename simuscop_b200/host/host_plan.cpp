@@ -70,17 +70,12 @@ void Job::generate_segments() {
 }
 
 // Segment::generateSegSequences, lib/segment/Segment.cpp:124-460
-void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<std::string>& haps) {
+// Copy-number phasing of a segment, the rand()-driven head of Segment::generateSegSequences (Segment.cpp:140-215):
+// which haplotype indices exist (CN < ploidy) or how many copies each carries, and which of them form the "major" set.
+// Runs once per segment (the first time its haplotypes are needed), in segment order: it consumes rand().
+void Job::phase_segment(Segment& seg) {
 	const int ploidy = cfg.num["ploidy"];
-	haps.assign(ploidy, std::string());
-	if (seg.CN == 0) die(1, "ERROR: copy number 0 segments are not supported (" + popu + " " + seg.chr + ":" + std::to_string(seg.start) + ")");
-	const std::string& chrSeq = fasta.chromosome(seg.chr);
-	const size_t refOff = (size_t)(seg.start - 1);
-	const size_t refLen = std::min((size_t)seg.refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
-	const char* ref = chrSeq.data() + refOff;
-	const unsigned int refSize = (unsigned int)refLen;
 	const int CN = seg.CN, mCN = seg.mCN;
-	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
 	if (seg.mIndx.empty()) {
 		if (CN < ploidy) {
 			for (int i = 0; i < CN; i++)
@@ -111,6 +106,20 @@ void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<st
 			}
 		}
 	}
+}
+
+void Job::build_haplotypes(Segment& seg, const std::string& popu, std::vector<std::string>& haps) {
+	const int ploidy = cfg.num["ploidy"];
+	haps.assign(ploidy, std::string());
+	if (seg.CN == 0) die(1, "ERROR: copy number 0 segments are not supported (" + popu + " " + seg.chr + ":" + std::to_string(seg.start) + ")");
+	const std::string& chrSeq = fasta.chromosome(seg.chr);
+	const size_t refOff = (size_t)(seg.start - 1);
+	const size_t refLen = std::min((size_t)seg.refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
+	const char* ref = chrSeq.data() + refOff;
+	const unsigned int refSize = (unsigned int)refLen;
+	const int CN = seg.CN;
+	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
+	phase_segment(seg);
 	if (CN < ploidy) {
 		for (int i = 0; i < ploidy; i++)
 			if (std::find(seg.seqReps.begin(), seg.seqReps.end(), i) != seg.seqReps.end()) haps[i].assign(ref, refLen);
@@ -305,6 +314,43 @@ double Job::weighted_length_from(Segment& seg, const std::vector<std::string>& h
 	return weights_from_gc(seg, specs, gc.data());
 }
 
+// A segment none of whose variants is an insertion or deletion: every haplotype is the reference slice repeated once per
+// copy with SNP / SNV alleles substituted (Segment.cpp:217-311), so the device can build it from the uploaded chromosome.
+bool Job::segment_is_copy_only(const Segment& seg, const std::string& popu) {
+	for (const Ins& in : inss[popu][seg.chr]) if (in.pos >= seg.start && in.pos <= seg.end) return false;
+	for (const Del& d : dels[popu][seg.chr]) if (d.pos >= seg.start && d.pos <= seg.end) return false;
+	return true;
+}
+
+// copies per haplotype index and the substitutions (haplotype, offset in the first copy, allele) in application order
+void Job::segment_copies_and_pokes(Segment& seg, const std::string& popu, std::vector<int>& reps, std::vector<Poke>& pokes) {
+	const int ploidy = cfg.num["ploidy"];
+	if (seg.CN == 0) die(1, "ERROR: copy number 0 segments are not supported (" + popu + " " + seg.chr + ":" + std::to_string(seg.start) + ")");
+	phase_segment(seg);
+	reps.assign(ploidy, 0);
+	for (int i = 0; i < ploidy; i++)
+		reps[i] = seg.CN < ploidy ? (std::find(seg.seqReps.begin(), seg.seqReps.end(), i) != seg.seqReps.end() ? 1 : 0) : seg.seqReps[i];
+	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
+	pokes.clear();
+	int k = 0;
+	auto sit = snps.find(seg.chr);
+	if (sit != snps.end())
+		for (const Snp& sn : sit->second)
+			if (sn.pos >= seg.start && sn.pos <= seg.end) {
+				for (int j = 0; j < ploidy; j++) if ((k == 0) == inM(j)) pokes.push_back(Poke{j, (long)(sn.pos - seg.start), sn.nucleotide});
+				k = (k + 1) % 2;
+			}
+	k = 0;
+	for (const Snv& sv : snvs[popu][seg.chr])
+		if (sv.pos >= seg.start && sv.pos <= seg.end) {
+			if (!sv.het) for (int j = 0; j < ploidy; j++) pokes.push_back(Poke{j, (long)(sv.pos - seg.start), sv.alt});
+			else {
+				for (int j = 0; j < ploidy; j++) if ((k == 0) == inM(j)) pokes.push_back(Poke{j, (long)(sv.pos - seg.start), sv.alt});
+				k = (k + 1) % 2;
+			}
+		}
+}
+
 // Device mode of the weights pass: the haplotype strings of one population are built chromosome by chromosome, appended
 // to the haplotype store(s) in contig order (for every haplotype index, the segments' strings in order) and dropped; the
 // GC percentages of all bins of the chromosome come from ssc_gc_census on the packed store.  Same bins, same draws in
@@ -312,6 +358,7 @@ double Job::weighted_length_from(Segment& seg, const std::vector<std::string>& h
 int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>& devs, uint64_t& localSize,
                         std::map<std::string, ChrLayout>& layout) {
 	const int ploidy = cfg.num["ploidy"];
+	const bool useRefBuild = !getenv("SIMUSCOP_HOST_HAPLOTYPES");   // debugging: build every haplotype string on the host
 	int rc = 0;
 	for (auto& chr : chroms) {
 		std::vector<Segment>& v = segs[popu][chr];
@@ -320,21 +367,56 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		L.hapLen.assign(v.size(), std::vector<size_t>(ploidy, 0));
 		L.contigEnd.assign(ploidy, 0);
 		double t0 = PhaseTimers::now();
+		// segments without indel variants are built on the device from the uploaded chromosome (copies + substitutions);
+		// the others as host strings (Segment::generateSegSequences' insert / erase arithmetic stays on the host)
+		const std::string& chrSeq = fasta.chromosome(chr);
 		std::vector<std::vector<std::string>> haps(v.size());
+		std::vector<std::vector<int>> reps(v.size());
+		std::vector<std::vector<Poke>> pokes(v.size());
+		std::vector<char> onDev(v.size(), 0);
+		std::vector<size_t> refOffs(v.size(), 0), refLens(v.size(), 0);
+		bool anyDev = false;
 		for (size_t k = 0; k < v.size(); k++) {
-			build_haplotypes(v[k], popu, haps[k]);
-			for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = haps[k][h].size();
+			const size_t refOff = (size_t)(v[k].start - 1);
+			const size_t refLen = std::min((size_t)v[k].refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
+			refOffs[k] = refOff; refLens[k] = refLen;
+			if (useRefBuild && refLen > 0 && segment_is_copy_only(v[k], popu)) {
+				segment_copies_and_pokes(v[k], popu, reps[k], pokes[k]);
+				for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = refLen * (size_t)reps[k][h];
+				onDev[k] = 1; anyDev = true;
+			} else {
+				build_haplotypes(v[k], popu, haps[k]);
+				for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = haps[k][h].size();
+			}
 		}
 		double t1 = PhaseTimers::now();
+		if (anyDev)
+			for (ssc_handle* dev : devs) { rc = ssc_reference_upload(dev, chrSeq.data(), chrSeq.size()); if (rc) return rc; }
+		std::vector<int64_t> pokePos; std::vector<char> pokeChr;
 		for (int h = 0; h < ploidy; h++) {
 			for (size_t k = 0; k < v.size(); k++) {
-				if (haps[k][h].empty()) continue;
+				if (L.hapLen[k][h] == 0) continue;
 				uint64_t first = localSize;
-				for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
+				if (onDev[k]) {
+					for (ssc_handle* dev : devs) { rc = ssc_genome_append_ref(dev, refOffs[k], refLens[k], reps[k][h], &first); if (rc) return rc; }
+					for (const Poke& pk : pokes[k])
+						if (pk.hap == h && (size_t)pk.off < refLens[k])
+							for (int t = 0; t < reps[k][h]; t++) { pokePos.push_back((int64_t)(first + (uint64_t)pk.off + (uint64_t)t * refLens[k])); pokeChr.push_back(pk.c); }
+				} else {
+					for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
+				}
 				L.base[k][h] = (int64_t)first;
-				localSize = first + haps[k][h].size();
+				localSize = first + L.hapLen[k][h];
 			}
 			L.contigEnd[h] = (int64_t)localSize;
+		}
+		if (!pokePos.empty()) {
+			// later substitutions of the same base win (SNP, then SNV): keep the last one per store index
+			std::map<int64_t, char> last;
+			for (size_t i = 0; i < pokePos.size(); i++) last[pokePos[i]] = pokeChr[i];
+			pokePos.clear(); pokeChr.clear();
+			for (auto& kv : last) { pokePos.push_back(kv.first); pokeChr.push_back(kv.second); }
+			for (ssc_handle* dev : devs) { rc = ssc_genome_poke(dev, pokePos.data(), pokeChr.data(), (int64_t)pokePos.size()); if (rc) return rc; }
 		}
 		haps.clear(); haps.shrink_to_fit();
 		double t2 = PhaseTimers::now();

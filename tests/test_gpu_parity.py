@@ -320,3 +320,35 @@ def test_many_tickets_per_warp(ctas, built, workdir):
             assert gzip.decompress(z1) == r1 and gzip.decompress(z2) == r2
         finally:
             g.close()
+
+
+@pytest.mark.parametrize("name", ["pe_variants", "se_tumor", "pe_ploidy3", "pe_xten"])
+def test_device_built_haplotypes_equal_host_strings(name, built, workdir):
+    """segments without indel variants are built on the device from the uploaded chromosome
+    (ssc_reference_upload / ssc_genome_append_ref / ssc_genome_poke: copies per copy-number phasing + SNP / SNV alleles);
+    the decoded store must equal the haplotype strings the host builds (the plan dump, pinned against the instrumented
+    reference by test_host_logic), base for base, for every sample."""
+    import os
+    import numpy as np
+    from simuscop_b200 import cuda_binding, host_binding, synth
+    scn = helpers.build_scenario(name, workdir)
+    d = scn["dir"]
+    cfg = os.path.join(d, "cfg_hap.txt")
+    synth.write_config(cfg, output=os.path.join(d, "out_hap"), **scn["kw"])
+    job = host_binding.Job(cfg, scn["seed"])
+    g = cuda_binding.Generator(0)
+    try:
+        for s in range(job.num_samples):
+            dump = os.path.join(d, "hap_%d.plan" % s)
+            job.prepare(s, g, dump)
+            plan = planfile.read_plan(dump)
+            want = np.frombuffer(bytes(plan.genome), np.uint8).copy()
+            want &= 0xDF                                                      # upper case
+            ok = (want == ord("A")) | (want == ord("C")) | (want == ord("G")) | (want == ord("T"))
+            want[~ok] = ord("N")
+            assert g.genome_size() == len(want)
+            got = np.frombuffer(g.genome_read(0, len(want)), np.uint8)
+            assert (got == want).all(), "first difference at store base %d" % int(np.flatnonzero(got != want)[0])
+    finally:
+        g.close()
+        job.close()

