@@ -855,7 +855,7 @@ int ssc_sub_lookup_host(const double* cdf4, uint32_t u) {
 }
 
 int64_t ssc_gzip_member_host(const uint8_t* in, uint32_t n, const uint8_t* sample, size_t sample_n, uint8_t* out, size_t cap) {
-	if (!in || !out || n < 4) return -1;
+	if (!in || !out || n < 8) return -1;
 	uint64_t hist[256];
 	memset(hist, 0, sizeof(hist));
 	for (size_t i = 0; i < sample_n; i++) hist[sample[i]]++;

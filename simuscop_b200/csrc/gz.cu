@@ -6,11 +6,12 @@
 // members, so the per-member cost is a ~60-byte block header.  Concatenated members are a valid .gz file
 // (SeqWriter's plain files, lib/seqwriter/SeqWriter.cpp:41-54, remain the default output).
 //
-// Kernel: one warp per (ticket, file).  A round takes 128 bytes (one 32-bit word per lane): LUT -> up to 60 bits
-// per lane, warp scan of the bit counts, OR into a shared-memory round buffer, coalesced store of the completed
-// words.  CRC-32 (the gzip trailer) is computed on the fly without a second pass: lane l keeps the pure remainder
-// of its strided words (slice-by-4 tables), advanced by 128 bytes of zeros per round through four 256-entry
-// tables of the linear map x^1024 mod P; the lanes are combined at the end with one GF(2) multiplication each.
+// Kernel: one warp per (ticket, file).  A round takes 256 bytes (two 32-bit words per lane): LUT -> up to 2 x 60 bits
+// per lane, warp scan of the bit counts, OR into a shared-memory round buffer (two buffers in turn: the one just
+// written out is zeroed word by word as it is stored), coalesced store of the completed words.  CRC-32 (the gzip
+// trailer) is computed on the fly without a second pass: lane l keeps the pure remainder of its strided word pairs
+// (slice-by-4 tables), advanced by 256 bytes of zeros per round through four 256-entry tables of the linear map
+// x^2048 mod P; the lanes are combined at the end with one GF(2) multiplication each.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -200,9 +201,9 @@ const char* gz_build_tables(const uint64_t hist[256], GzTables* t) {
 	for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ GZ_POLY : c >> 1; t->crcT[0][i] = c; }
 	for (int k = 1; k < 4; k++)
 		for (uint32_t i = 0; i < 256; i++) t->crcT[k][i] = t->crcT[0][t->crcT[k - 1][i] & 0xff] ^ (t->crcT[k - 1][i] >> 8);
-	const uint32_t x1024 = h_xpow8(128);                 // advance a remainder by 128 zero bytes
+	const uint32_t x2048 = h_xpow8(256);                 // advance a remainder by 256 zero bytes
 	for (int k = 0; k < 4; k++)
-		for (uint32_t i = 0; i < 256; i++) t->crcS[k][i] = h_multmodp(x1024, i << (8 * k));
+		for (uint32_t i = 0; i < 256; i++) t->crcS[k][i] = h_multmodp(x2048, i << (8 * k));
 	for (uint32_t n = 0; n < 256; n++) t->xp[n] = h_xpow8(n);
 	return "";
 }
@@ -210,7 +211,7 @@ const char* gz_build_tables(const uint64_t hist[256], GzTables* t) {
 // Host mirror of deflate_blobs_kernel for one blob (same tables, same lane-strided CRC arithmetic, same bit packing):
 // lets the table construction and the CRC algebra be checked against zlib without a GPU.  Returns the member size or 0.
 size_t gz_member_host(const GzTables* t, const uint8_t* src, uint32_t len, uint8_t* dst, size_t cap) {
-	if (len < 4) return 0;
+	if (len < 8) return 0;
 	std::vector<uint32_t> out(t->prefix, t->prefix + ((t->prefixBits + 31) >> 5));
 	uint64_t bits = t->prefixBits;
 	auto put = [&](uint64_t v, uint32_t n) {
@@ -220,22 +221,24 @@ size_t gz_member_host(const GzTables* t, const uint8_t* src, uint32_t len, uint8
 		}
 	};
 	if (t->prefixBits & 31u) out.back() &= (1u << (t->prefixBits & 31u)) - 1u;
-	const uint32_t W = len >> 2;
+	const uint32_t W = len >> 2, P2 = W >> 1;          // full word pairs; an odd last word goes with the tail bytes
 	uint32_t A[32], last[32];
 	for (int l = 0; l < 32; l++) { A[l] = 0; last[l] = 0xFFFFFFFFu; }
-	for (uint32_t idx = 0; idx < W; idx++) {
-		uint32_t wv; memcpy(&wv, src + 4 * (size_t)idx, 4);
-		const int l = idx & 31;
+	auto step = [&](uint32_t c) { return t->crcT[3][c & 0xff] ^ t->crcT[2][(c >> 8) & 0xff] ^ t->crcT[1][(c >> 16) & 0xff] ^ t->crcT[0][c >> 24]; };
+	for (uint32_t pi = 0; pi < P2; pi++) {
+		uint32_t w0, w1; memcpy(&w0, src + 8 * (size_t)pi, 4); memcpy(&w1, src + 8 * (size_t)pi + 4, 4);
+		const int l = pi & 31;
 		uint32_t c = A[l];
 		c = t->crcS[0][c & 0xff] ^ t->crcS[1][(c >> 8) & 0xff] ^ t->crcS[2][(c >> 16) & 0xff] ^ t->crcS[3][c >> 24];
-		const uint32_t wc = idx == 0 ? ~wv : wv;
-		A[l] = c ^ t->crcT[3][wc & 0xff] ^ t->crcT[2][(wc >> 8) & 0xff] ^ t->crcT[1][(wc >> 16) & 0xff] ^ t->crcT[0][wc >> 24];
-		last[l] = idx;
-		for (int k = 0; k < 4; k++) { const uint32_t e = t->lut[(wv >> (8 * k)) & 0xff]; put(e & 0xffffu, e >> 16); }
+		A[l] = c ^ step(step(pi == 0 ? ~w0 : w0) ^ w1);
+		last[l] = pi;
+		for (int k = 0; k < 4; k++) { const uint32_t e = t->lut[(w0 >> (8 * k)) & 0xff]; put(e & 0xffffu, e >> 16); }
+		for (int k = 0; k < 4; k++) { const uint32_t e = t->lut[(w1 >> (8 * k)) & 0xff]; put(e & 0xffffu, e >> 16); }
 	}
 	uint32_t crc = 0;
-	for (int l = 0; l < 32; l++) if (last[l] != 0xFFFFFFFFu) crc ^= h_multmodp(t->xp[(W - 1 - last[l]) * 4], A[l]);
-	for (uint32_t i = W * 4; i < len; i++) { crc = t->crcT[0][(crc ^ src[i]) & 0xff] ^ (crc >> 8); const uint32_t e = t->lut[src[i]]; put(e & 0xffffu, e >> 16); }
+	for (int l = 0; l < 32; l++) if (last[l] != 0xFFFFFFFFu) crc ^= h_multmodp(t->xp[(P2 - 1 - last[l]) * 8], A[l]);
+	if (P2 == 0) crc = 0xFFFFFFFFu;                      // fewer than 8 bytes: plain byte-wise CRC from the initial value
+	for (uint32_t i = P2 * 8; i < len; i++) { crc = t->crcT[0][(crc ^ src[i]) & 0xff] ^ (crc >> 8); const uint32_t e = t->lut[src[i]]; put(e & 0xffffu, e >> 16); }
 	crc = ~crc;
 	put(t->lut[256] & 0xffffu, t->lut[256] >> 16);
 	while (bits & 7) put(0, 1);
@@ -250,7 +253,7 @@ size_t gz_member_host(const GzTables* t, const uint8_t* src, uint32_t len, uint8
 // device
 // ------------------------------------------------------------------------------------------------
 static constexpr int GZ_WARPS = 8;
-static constexpr int GZ_RB = 72;            // round buffer words: 31 carry bits + 32 * 60 < 62 words (+ slack for the trailer round)
+static constexpr int GZ_RB = 128;           // round buffer words: 31 carry bits + 32 lanes * 120 bits < 122 words (+ the trailer round)
 
 __device__ __forceinline__ uint32_t d_multmodp(uint32_t a, uint32_t b) {
 	uint32_t p = 0;
@@ -282,94 +285,113 @@ __global__ void __launch_bounds__(GZ_WARPS * 32) deflate_blobs_kernel(const uint
 	__shared__ uint32_t s_S[4][256];
 	__shared__ uint32_t s_xp[256];
 	__shared__ uint32_t s_prefix[GZ_PREFIX_WORDS];
-	__shared__ uint32_t s_rb[GZ_WARPS][GZ_RB];
+	__shared__ uint32_t s_rb[GZ_WARPS][2][GZ_RB];
 	for (int i = threadIdx.x; i < 257; i += blockDim.x) s_lut[i] = tab->lut[i];
 	for (int i = threadIdx.x; i < 1024; i += blockDim.x) { (&s_T[0][0])[i] = (&tab->crcT[0][0])[i]; (&s_S[0][0])[i] = (&tab->crcS[0][0])[i]; }
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_xp[i] = tab->xp[i];
 	for (int i = threadIdx.x; i < GZ_PREFIX_WORDS; i += blockDim.x) s_prefix[i] = tab->prefix[i];
+	for (int i = threadIdx.x; i < GZ_WARPS * 2 * GZ_RB; i += blockDim.x) (&s_rb[0][0][0])[i] = 0u;
 	__syncthreads();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t* rb = s_rb[warp];
+	uint32_t* rbA = s_rb[warp][0];              // buffer of the current round: all zero except its first word (the carry)
+	uint32_t* rbB = s_rb[warp][1];              // all zero
 	const uint32_t prefixBits = tab->prefixBits;
 	const int nWarps = gridDim.x * GZ_WARPS;
+	auto crc_step = [&](uint32_t c) { return s_T[3][c & 0xff] ^ s_T[2][(c >> 8) & 0xff] ^ s_T[1][(c >> 16) & 0xff] ^ s_T[0][c >> 24]; };
 	for (int job = blockIdx.x * GZ_WARPS + warp; job < 2 * nTiles; job += nWarps) {
 		const int ticket = job >> 1, file = job & 1;
 		const unsigned long long lens = rawLens[ticket];
 		const uint32_t len = file ? (uint32_t)(lens & 0x7fffffffull) : (uint32_t)(lens >> 31);
 		uint32_t outBytes = 0;
-		if (len >= 4) {
-			const uint32_t* src32 = (const uint32_t*)((file ? raw2 : raw1) + (size_t)ticket * rawPitch);
-			const uint8_t* src8 = (const uint8_t*)src32;
+		if (len >= 8) {
+			const uint2* src64 = (const uint2*)((file ? raw2 : raw1) + (size_t)ticket * rawPitch);
+			const uint8_t* src8 = (const uint8_t*)src64;
 			uint32_t* dst32 = (uint32_t*)((file ? gz2 : gz1) + (size_t)ticket * gzPitch);
 			// ---- member header + block header
 			uint32_t outWords = prefixBits >> 5, carryBits = prefixBits & 31u;
 			for (uint32_t i = lane; i < outWords; i += 32) dst32[i] = s_prefix[i];
-			uint32_t carryWord = carryBits ? (s_prefix[outWords] & ((1u << carryBits) - 1u)) : 0u;
-			// ---- the words of the blob
-			const uint32_t W = len >> 2;
+			if (lane == 0) rbA[0] = carryBits ? (s_prefix[outWords] & ((1u << carryBits) - 1u)) : 0u;
+			__syncwarp();
+			// ---- the word pairs of the blob
+			const uint32_t P2 = len >> 3;
 			uint32_t A = 0, lastIdx = 0xFFFFFFFFu;
 			bool overflow = false;
-			for (uint32_t base = 0; base < W; base += 32) {
+			for (uint32_t base = 0; base < P2; base += 32) {
 				const uint32_t idx = base + lane;
-				const bool valid = idx < W;
-				const uint32_t wv = valid ? src32[idx] : 0u;
-				unsigned long long acc = 0;
-				uint32_t n = 0;
+				const bool valid = idx < P2;
+				unsigned long long acc0 = 0, acc1 = 0;
+				uint32_t n0 = 0, n1 = 0;
 				if (valid) {
-					// CRC: pure remainder of this lane's strided words; the 0xFFFFFFFF initial value = inverting the first word
+					const uint2 wv = src64[idx];
+					// CRC: pure remainder of this lane's strided word pairs; the 0xFFFFFFFF initial value = inverting the first word
 					uint32_t c = A;
 					c = s_S[0][c & 0xff] ^ s_S[1][(c >> 8) & 0xff] ^ s_S[2][(c >> 16) & 0xff] ^ s_S[3][c >> 24];
-					const uint32_t wc = idx == 0 ? ~wv : wv;
-					A = c ^ s_T[3][wc & 0xff] ^ s_T[2][(wc >> 8) & 0xff] ^ s_T[1][(wc >> 16) & 0xff] ^ s_T[0][wc >> 24];
+					A = c ^ crc_step(crc_step(idx == 0 ? ~wv.x : wv.x) ^ wv.y);
 					lastIdx = idx;
 #pragma unroll
 					for (int k = 0; k < 4; k++) {
-						const uint32_t e = s_lut[(wv >> (8 * k)) & 0xffu];
-						acc |= (unsigned long long)(e & 0xffffu) << n;
-						n += e >> 16;
+						const uint32_t e = s_lut[(wv.x >> (8 * k)) & 0xffu];
+						acc0 |= (unsigned long long)(e & 0xffffu) << n0;
+						n0 += e >> 16;
+					}
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint32_t e = s_lut[(wv.y >> (8 * k)) & 0xffu];
+						acc1 |= (unsigned long long)(e & 0xffffu) << n1;
+						n1 += e >> 16;
 					}
 				}
+				const uint32_t n = n0 + n1;
 				uint32_t incl = n;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
 				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				for (int i = lane; i < GZ_RB; i += 32) rb[i] = i == 0 ? carryWord : 0u;
-				__syncwarp();
-				put_bits(rb, carryBits + incl - n, acc, n);
+				const uint32_t off = carryBits + incl - n;
+				put_bits(rbA, off, acc0, n0);
+				put_bits(rbA, off + n0, acc1, n1);
 				__syncwarp();
 				const uint32_t totalBits = carryBits + total, nw = totalBits >> 5;
 				if ((outWords + nw + GZ_RB) * 4u > gzPitch) { overflow = true; break; }
-				for (uint32_t i = lane; i < nw; i += 32) dst32[outWords + i] = rb[i];
-				carryWord = rb[nw];
+				// store the completed words, zero them, and move the partial last word to the other (all zero) buffer
+				for (uint32_t i = lane; i <= nw; i += 32) {
+					const uint32_t v = rbA[i];
+					rbA[i] = 0u;
+					if (i < nw) dst32[outWords + i] = v; else rbB[0] = v;
+				}
+				__syncwarp();
+				{ uint32_t* tswap = rbA; rbA = rbB; rbB = tswap; }
 				carryBits = totalBits & 31u;
 				outWords += nw;
-				__syncwarp();
 			}
 			if (overflow) {
 				if (lane == 0) atomicOr(errorFlags, 8u);
+				for (int i = lane; i < GZ_RB; i += 32) { rbA[i] = 0u; rbB[i] = 0u; }
+				__syncwarp();
 			} else {
 				// ---- CRC of the whole blob
-				uint32_t part = lastIdx != 0xFFFFFFFFu ? d_multmodp(s_xp[(W - 1u - lastIdx) * 4u], A) : 0u;   // advance to the last word
+				uint32_t part = lastIdx != 0xFFFFFFFFu ? d_multmodp(s_xp[(P2 - 1u - lastIdx) * 8u], A) : 0u;   // advance to the last pair
 #pragma unroll
 				for (int d = 16; d > 0; d >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, d);
 				uint32_t crc = part;
-				for (uint32_t i = W * 4u; i < len; i++) crc = s_T[0][(crc ^ src8[i]) & 0xff] ^ (crc >> 8);
+				for (uint32_t i = P2 * 8u; i < len; i++) crc = s_T[0][(crc ^ src8[i]) & 0xff] ^ (crc >> 8);
 				crc = ~crc;
-				// ---- tail bytes, end of block, byte alignment, trailer (CRC32, ISIZE)
-				for (int i = lane; i < GZ_RB; i += 32) rb[i] = i == 0 ? carryWord : 0u;
-				__syncwarp();
-				unsigned long long acc = 0;
-				uint32_t n = 0;
-				for (uint32_t i = W * 4u; i < len; i++) { const uint32_t e = s_lut[src8[i]]; acc |= (unsigned long long)(e & 0xffffu) << n; n += e >> 16; }
-				{ const uint32_t e = s_lut[256]; acc |= (unsigned long long)(e & 0xffffu) << n; n += e >> 16; }
-				const uint32_t dataEnd = carryBits + n;
+				// ---- tail bytes (< 8), end of block, byte alignment, trailer (CRC32, ISIZE)
+				unsigned long long accA = 0, accB = 0;
+				uint32_t nA = 0, nB = 0;
+				for (uint32_t i = P2 * 8u; i < len; i++) {
+					const uint32_t e = s_lut[src8[i]];
+					if (i < P2 * 8u + 4u) { accA |= (unsigned long long)(e & 0xffffu) << nA; nA += e >> 16; }
+					else { accB |= (unsigned long long)(e & 0xffffu) << nB; nB += e >> 16; }
+				}
+				{ const uint32_t e = s_lut[256]; accB |= (unsigned long long)(e & 0xffffu) << nB; nB += e >> 16; }   // <= 3 literals + end of block
+				const uint32_t dataEnd = carryBits + nA + nB;
 				const uint32_t trailerAt = (dataEnd + 7u) & ~7u;
-				if (lane == 0) put_bits(rb, carryBits, acc, n);
-				if (lane == 1) put_bits(rb, trailerAt, (unsigned long long)crc | ((unsigned long long)len << 32), 64);
+				if (lane == 0) { put_bits(rbA, carryBits, accA, nA); put_bits(rbA, carryBits + nA, accB, nB); }
+				if (lane == 1) put_bits(rbA, trailerAt, (unsigned long long)crc | ((unsigned long long)len << 32), 64);
 				__syncwarp();
 				const uint32_t totalBits = trailerAt + 64u;
 				const uint32_t nw = (totalBits + 31u) >> 5;
-				for (uint32_t i = lane; i < nw; i += 32) dst32[outWords + i] = rb[i];
+				for (uint32_t i = lane; i < nw; i += 32) { dst32[outWords + i] = rbA[i]; rbA[i] = 0u; }
 				outBytes = outWords * 4u + (totalBits >> 3);
 				__syncwarp();
 			}

@@ -120,6 +120,17 @@ def test_cli_sharded_over_two_handles_is_byte_identical(built, workdir):
         outs[tag] = (helpers.read_file(os.path.join(out, "test_1.fq")), helpers.read_file(os.path.join(out, "test_2.fq")))
         assert sorted(os.listdir(out)) == ["test_1.fq", "test_2.fq"]
     assert outs["one"] == outs["three"] and len(outs["one"][0]) > 0
+    # the same sharded run with gzip output: the shard files are concatenated gzip members, a valid .gz of the same bytes
+    import gzip
+    out = os.path.join(d, "out_sh_gz")
+    cfg = os.path.join(d, "cfg_sh_gz.txt")
+    synth.write_config(cfg, output=out, **scn["kw"])
+    env = dict(os.environ, SIMUSCOP_SEED=str(scn["seed"]), SIMUSCOP_BATCH_PAIRS="8192", SIMUSCOP_DEVICES=devs, SIMUSCOP_GZIP="1")
+    r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert sorted(os.listdir(out)) == ["test_1.fq.gz", "test_2.fq.gz"]
+    assert gzip.decompress(helpers.read_file(os.path.join(out, "test_1.fq.gz"))) == outs["one"][0]
+    assert gzip.decompress(helpers.read_file(os.path.join(out, "test_2.fq.gz"))) == outs["one"][1]
 
 
 @pytest.mark.parametrize("name", sorted(helpers.STRESS))
