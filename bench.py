@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--workdir", default=os.environ.get("SIMUSCOP_BENCH_DIR", "/tmp/simuscop_bench"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gzip", action="store_true", help="skip the gzip end-to-end leg")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     a = ap.parse_args()
     if a.impl == "reference":
@@ -221,6 +222,23 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated (first touch decides the NUMA
+    # node of the FASTQ slabs; with 8 ranks the device->host stream is otherwise limited by cross-socket traffic)
+    affinity = None
+    all_cpus = os.sched_getaffinity(0)
+    if not a.no_affinity:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local)
+            try:
+                hnd = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            except Exception:
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(hnd)
+            affinity = len(os.sched_getaffinity(0))
+        except Exception as ex:  # informational only
+            affinity = "unavailable: %s" % type(ex).__name__
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -370,7 +388,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "synthetic %.2f Gb genome (24 chromosomes), %dx PE%d WGS, %s profile, insertSize 300, "
                                    "diploid, no SNP/variation" % (genome_len / 1e9, a.coverage, job.read_length, a.profile),
-                       "planned_pairs": planned, "batch_pairs": a.batch_pairs, "seed": 1,
+                       "planned_pairs": planned, "batch_pairs": a.batch_pairs, "seed": 1, "cpu_affinity_cpus": affinity,
                        "l2": "inputs larger than L2: every step reads fresh fragments of a %.1f GB packed haplotype store and writes "
                              "a fresh %.1f GB slab" % (2 * genome_len * 0.375 / 1e9, st["fastq_bytes"] / a.steps / 1e9),
                        "setup_s": {"fasta": round(t_fasta, 2), "host_plan_and_upload": round(t_plan, 2)},
@@ -399,6 +417,7 @@ def main():
                                  "per step at ~80 % of the copy bandwidth; see DESIGN.md"},
         }
         if world == 1 and not a.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)          # the reference gets every host core again
             threads = os.cpu_count() or 1
             from simuscop_b200 import paths
             try:

@@ -51,7 +51,7 @@ static constexpr int F_LUT_N = 6 * 64;          // context LUT (16-bit entries: 
 
 struct FastLayout {
 	int sub, qual, qualSym, isizeT, isizeSym, insT, insSym, delT, delSym, lut, dig, warp, total;
-	int w_src, w_ev, w_insb, w_win, w_hdr, perWarp;
+	int w_ev, w_insb, w_win, w_hdr, perWarp;
 };
 
 __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
@@ -69,8 +69,7 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 	L.lut = o; o += F_LUT_N * 2;
 	L.dig = o; o += 32 * 16;                       // per-lane header digit constants
 	int w = 0;
-	L.w_src = w; w += F_SRC_CAP;
-	L.w_ev = w; w += F_EV_MAX * 4;
+	L.w_ev = w; w += F_EV_MAX * 8;
 	L.w_insb = w; w += F_INS_CAP;
 	L.w_win = w; w += 2 * F_WIN_WORDS * 4;          // one window per mate, filled by cp.async
 	L.w_hdr = w; w += 96;                           // record header of the current pair
@@ -202,7 +201,7 @@ struct WarpCtx {
 	const uint32_t* delT; const uint16_t* delSym;
 	const uint32_t* win;       // shared window: data words [0..16), mask words [16..25)
 	const uint8_t* lutB;       // shared: context LUT (16-bit entries, 6 variants of 64)
-	uint8_t* src; uint32_t* ev; uint8_t* insb;
+	uint32_t* ev; uint8_t* insb;
 	const uint32_t* rk;        // Philox round keys
 	uint32_t c0, c1;           // pair counter words
 	uint32_t qualBaseS;        // shared address folded into word 3 of the substitution rows
@@ -254,10 +253,24 @@ __device__ __forceinline__ uint32_t window_code(const WarpCtx& w, int relBase /*
 	return code;
 }
 
+// cooperative lower bound in a compressed CDF held in shared memory (warp-uniform u, all lanes converged):
+// sym[#{i < n-1 : T[i] < u}] -- the same index uni_lookup finds, one ballot per 32 thresholds
+__device__ __forceinline__ int coop_lookup(const uint32_t* T, const uint16_t* sym, int n, uint32_t u, int lane) {
+	int cnt = 0;
+	for (int b = 0; b < n - 1; b += 32) {
+		const int i = b + lane;
+		cnt += __popc(__ballot_sync(0xffffffffu, i < n - 1 && T[i] < u));
+	}
+	return (int)sym[cnt];
+}
+
 // Slow path of Profile::predict (a read with an indel candidate or a non-ACGT base): compact, not unrolled.
 // evbits: per lane, bit 2c = insertion test hit at cycle 32c+lane, bit 2c+1 = deletion test hit.
 // x2/x3: the substitution / quality draws of output positions 32c+lane, c < NCH (registers of the caller).
-// Writes bases/quals into stage[H ..]; returns m.
+// The post-indel source sequence (Profile.cpp:1636-1658) is never materialised: the events are kept as a sorted list of
+// output-coordinate segments {first output position, inserted bases, template shift behind it}; every lane maps its
+// output position to a template base of the packed window (or an inserted base) and gets the two context bases from its
+// neighbours by shuffle.  Writes bases/quals into stage[H ..]; returns m.
 template <int NCH, int QP>
 __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int mate, bool rev, int relFirst,
                                       uint8_t* stage, int H, unsigned int* errorFlags,
@@ -267,7 +280,11 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 	const uint32_t c2cyc = ((uint32_t)mate << 28) | ((uint32_t)STREAM_CYCLE << 24);
 	const uint32_t c2len = ((uint32_t)mate << 28) | ((uint32_t)STREAM_LEN << 24);
 	const uint32_t c2ins = ((uint32_t)mate << 28) | ((uint32_t)STREAM_INSBASE << 24);
-	int nEv = 0, insTotal = 0, indelLength = 0, skipUntil = 0;
+	// event k: x = first output position behind the event's template base | inserted bases << 9 | their offset in insb << 17,
+	//          y = output position - template position of everything behind the event (running indelLength)
+	uint2* evs = (uint2*)w.ev;
+	uint2 e0 = make_uint2(0u, 0u);
+	int nEv = 0, insTotal = 0, cum = 0, skipUntil = 0;
 	bool tooMany = false;
 	for (int c = 0; c < chunksRL; c++) {
 		const uint32_t insMask = __ballot_sync(0xffffffffu, (evbits >> (2 * c)) & 1u);
@@ -280,7 +297,7 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 			if (j < skipUntil) continue;
 			const u32x4 lb = philox_rk(w.c0, w.c1, c2len, (uint32_t)j, w.rk);
 			if ((insMask >> bit) & 1u) {
-				const int Lk = uni_lookup(w.insT, w.insSym, w.nInsLen, lb.x);          // Profile::getInsertLen
+				const int Lk = coop_lookup(w.insT, w.insSym, w.nInsLen, lb.x, lane);     // Profile::getInsertLen
 				if (Lk > 0) {
 					if (nEv >= F_EV_MAX || insTotal + Lk > F_INS_CAP) { tooMany = true; break; }
 					for (int i = lane; i < Lk; i += 32) {                                  // Profile.cpp:1563-1566
@@ -288,114 +305,104 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 						const uint32_t ws = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
 						w.insb[insTotal + i] = (uint8_t)__umulhi((uint32_t)w.nBasesM1, ws);
 					}
-					if (lane == 0) w.ev[nEv] = (uint32_t)j | ((uint32_t)Lk << 12) | ((uint32_t)insTotal << 20) | (1u << 31);
-					nEv++; insTotal += Lk; indelLength += Lk;
+					// the inserted bases follow template base j (Profile.cpp:1650-1656)
+					const uint2 e = make_uint2((uint32_t)(j + cum + 1) | ((uint32_t)Lk << 9) | ((uint32_t)insTotal << 17), (uint32_t)(cum + Lk));
+					if (nEv == 0) e0 = e; else if (lane == 0) evs[nEv] = e;
+					nEv++; insTotal += Lk; cum += Lk;
 				}
 			} else {
-				int Lk = uni_lookup(w.delT, w.delSym, w.nDelLen, lb.y);                  // Profile::getDelLen
+				int Lk = coop_lookup(w.delT, w.delSym, w.nDelLen, lb.y, lane);           // Profile::getDelLen
 				if (Lk > RL - j) Lk = RL - j;                                             // Profile.cpp:1613
 				if (Lk > 0) {
 					if (nEv >= F_EV_MAX) { tooMany = true; break; }
-					if (lane == 0) w.ev[nEv] = (uint32_t)j | ((uint32_t)Lk << 12);
-					nEv++; indelLength -= Lk; skipUntil = j + Lk;
+					const uint2 e = make_uint2((uint32_t)(j + cum), (uint32_t)(cum - Lk));
+					if (nEv == 0) e0 = e; else if (lane == 0) evs[nEv] = e;
+					nEv++; cum -= Lk; skipUntil = j + Lk;
 				}
 			}
 		}
 	}
-	if (RL + indelLength < 50) { nEv = 0; indelLength = 0; }                             // Profile.cpp:1627-1634
-	int m = RL + indelLength;
+	if (RL + cum < 50) { nEv = 0; cum = 0; }                                             // Profile.cpp:1627-1634
+	int m = RL + cum;
 	if (tooMany || m > F_SRC_CAP) {
 		if (lane == 0) atomicOr(errorFlags, tooMany ? 4u : 2u);
 		nEv = 0; m = RL;
 	}
 	__syncwarp();
-	// source sequence: template bases moved to their output positions, inserted bases after their base
-	for (int c = 0; c < chunksRL; c++) {
-		const int j = c * 32 + lane;
-		if (j < RL) {
-			const uint32_t code = window_code(w, rev ? relFirst - j : relFirst + j, rev);
-			int shift = 0; bool dropped = false;
-			for (int k = 0; k < nEv; k++) {
-				const uint32_t ev = w.ev[k];
-				const int ej = (int)(ev & 0xfffu), el = (int)((ev >> 12) & 0xffu);
-				if (ev >> 31) { if (ej < j) shift += el; }
-				else { if (j >= ej && j < ej + el) dropped = true; else if (j >= ej + el) shift -= el; }
-			}
-			if (!dropped) w.src[j + shift] = (uint8_t)code;
-		}
-	}
-	int cum = 0;
-	for (int k = 0; k < nEv; k++) {
-		const uint32_t ev = w.ev[k];
-		const int ej = (int)(ev & 0xfffu), el = (int)((ev >> 12) & 0xffu);
-		if (ev >> 31) {
-			const int io = (int)((ev >> 20) & 0x7ffu);
-			for (int i = lane; i < el; i += 32) w.src[ej + cum + 1 + i] = w.insb[io + i];
-			cum += el;
-		} else cum -= el;
-	}
-	__syncwarp();
-	// ---- re-pack the post-indel read (2-bit codes + non-ACGT flags, 16 pad bases in front) so that the per-base work
-	// below is the fast path's: context cut out of packed words, LUT -> substitution row -> quality row
-	uint32_t* pk = (uint32_t*)w.insb;                // 18 words: the inserted bases are not needed any more
-	uint32_t* pkN = pk + 18;                         // 10 words
-	{
-		const uint32_t* s32 = (const uint32_t*)w.src;
-		const uint32_t a0 = s32[2 * lane], a1 = s32[2 * lane + 1];
-		// byte i of a word holds one base: gather the low two bits (code) / bit 2 (non-ACGT) of the four bytes by multiplication
-		const uint32_t c8 = (((a0 & 0x03030303u) * 0x01041040u) >> 24) | ((((a1 & 0x03030303u) * 0x01041040u) >> 24) << 8);
-		const uint32_t n8 = ((((a0 >> 2) & 0x01010101u) * 0x01020408u) >> 24) | (((((a1 >> 2) & 0x01010101u) * 0x01020408u) >> 24) << 4);
-		__syncwarp();                                // every lane has read its inserted bases / source bytes
-		((uint16_t*)pk)[2 + lane] = (uint16_t)c8;
-		((uint8_t*)pkN)[4 + lane] = (uint8_t)n8;
-		if (lane == 0) { pk[0] = 0u; pkN[0] = 0u; }
-	}
-	__syncwarp();
 	const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
 	const int chunksM = (m + 31) >> 5;
-	auto emit = [&](int j, uint32_t u2, uint32_t u3) {
-		const int rb = 14 + j, nb = 30 + j;          // first of the three context bases / of their flags
-		const uint32_t v6 = __funnelshift_r(pk[rb >> 4], pk[(rb >> 4) + 1], (uint32_t)(rb & 15) * 2u) & 63u;
-		const uint32_t n3 = __funnelshift_r(pkN[nb >> 5], pkN[(nb >> 5) + 1], (uint32_t)(nb & 31)) & 7u;   // bit 2 = the base itself
-		const uint32_t var = j >= 2 ? 0u : (j == 0 ? 2u : 3u);                                            // 'X' padded contexts
-		const uint32_t rowIdx = *(const uint16_t*)(w.lutB + var * 128u + v6 * 2u);
-		const uint32_t binIdx = __umulhi((uint32_t)(j * w.B), inv);
-		const uint4 sr = w.sub[rowIdx + binIdx];
-		const uint32_t cur = v6 >> 4;
-		uint32_t acc = sr.w;
-		add_gt(acc, u2, sr.x, (uint32_t)F_QROW); add_gt(acc, u2, sr.y, (uint32_t)F_QROW); add_gt(acc, u2, sr.z, (uint32_t)F_QROW);
-		if (n3) acc = w.qualBaseS + cur * (5u * F_QROW);                       // unknown context: the base passes through
-		uint32_t ch, q;
-		if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
-		else if (QP == 8) {
-			uint32_t qa = binIdx * (16u * F_QROW) + acc;
-			add_lt(qa, lds_u32(qa + 24), u3, 32u);
-			add_lt(qa, lds_u32(qa + 8), u3, 16u);
-			add_lt(qa, lds_u32(qa), u3, 8u);
-			q = lds_u8(qa + 4);
-			ch = lds_u8(qa + 5);
-		} else {
-			const uint32_t r16 = acc / (uint32_t)F_QROW;                       // qualBaseS == 0 here
-			q = qual_lookup<QP>(w.q, r16 >> 2, r16 & 3u, binIdx, w.B, u3);
-			ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
-		}
-		stage[H + j] = (uint8_t)ch;
-		stage[H + m + 3 + j] = (uint8_t)q;
-	};
-	// the draws of the first NCH chunks are the caller's registers; select by chunk without dynamic indexing
-	// (kept rolled: the hot loop has to stay inside the instruction cache)
+	uint32_t prev = 0;                               // codes of the previous chunk ('X' pads in front of the read: code 0, no flag)
+	// the first event (almost always the only one) stays in registers: every lane computed it
+	const int e0start = nEv > 0 ? (int)(e0.x & 0x1ffu) : 0x7fffffff;
+	const int e0ins = (int)((e0.x >> 9) & 0xffu), e0off = (int)(e0.x >> 17), e0shift = (int)e0.y;
+	uint8_t* const stB = stage + H + lane;          // bases of this lane; the qualities follow m + 3 bytes later
+	// the draws of the first NCH chunks are the caller's registers: taken from the front of a copy that is shifted down
+	// by one chunk per iteration (kept rolled: the hot loop has to stay inside the instruction cache)
+	uint32_t a2[NCH], a3[NCH];
+#pragma unroll
+	for (int k = 0; k < NCH; k++) { a2[k] = x2[k]; a3[k] = x3[k]; }
 #pragma unroll 1
 	for (int c = 0; c < chunksM; c++) {
 		const int j = c * 32 + lane;
-		uint32_t u2 = 0, u3 = 0;
-		if (c < NCH) {
+		uint32_t u2 = a2[0], u3 = a3[0];
 #pragma unroll
-			for (int k = 0; k < NCH; k++) if (k == c) { u2 = x2[k]; u3 = x3[k]; }
-		} else if (j < m) {
+		for (int k = 0; k + 1 < NCH; k++) { a2[k] = a2[k + 1]; a3[k] = a3[k + 1]; }
+		if (c >= NCH && j < m) {
 			const u32x4 blk = philox_rk(w.c0, w.c1, c2cyc, (uint32_t)j, w.rk);
 			u2 = blk.z; u3 = blk.w;
 		}
-		if (j < m) emit(j, u2, u3);
+		// source base of output position j: the last event segment that starts at or before j decides
+		int shift = 0, insIdx = -1;
+		{
+			const int d = j - e0start;
+			if (d >= 0) { shift = e0shift; insIdx = d < e0ins ? e0off + d : -1; }
+		}
+#pragma unroll 1
+		for (int k = 1; k < nEv; k++) {
+			const uint2 e = evs[k];
+			const int d = j - (int)(e.x & 0x1ffu);
+			if (d >= 0) {
+				shift = (int)e.y;
+				insIdx = d < (int)((e.x >> 9) & 0xffu) ? (int)(e.x >> 17) + d : -1;
+			}
+		}
+		int tpos = j - shift;                            // lanes past the read end / on inserted bases: any valid window index
+		tpos = tpos < 0 ? 0 : (tpos > RL - 1 ? RL - 1 : tpos);
+		uint32_t code = window_code(w, rev ? relFirst - tpos : relFirst + tpos, rev);   // 0..3, 4 = non-ACGT
+		if (insIdx >= 0) code = w.insb[insIdx];
+		// the two bases in front (Profile.cpp:1660-1666): lanes 0 and 1 take them from the previous chunk
+		const uint32_t both = code | (prev << 4);
+		const uint32_t r1 = __shfl_sync(0xffffffffu, both, (lane + 31) & 31), r2 = __shfl_sync(0xffffffffu, both, (lane + 30) & 31);
+		const uint32_t p1 = lane >= 1 ? (r1 & 7u) : (r1 >> 4), p2 = lane >= 2 ? (r2 & 7u) : (r2 >> 4);
+		prev = code;
+		if (j < m) {
+			const uint32_t cur = code & 3u;
+			const uint32_t v6 = (p2 & 3u) | ((p1 & 3u) << 2) | (cur << 4);
+			const uint32_t n3 = (p2 >> 2) | ((p1 >> 2) << 1) | ((code >> 2) << 2);          // bit 2 = the base itself
+			const uint32_t var = j >= 2 ? 0u : (j == 0 ? 2u : 3u);                          // 'X' padded contexts
+			const uint32_t rowIdx = *(const uint16_t*)(w.lutB + var * 128u + v6 * 2u);
+			const uint32_t binIdx = __umulhi((uint32_t)(j * w.B), inv);
+			const uint4 sr = w.sub[rowIdx + binIdx];
+			uint32_t acc = sr.w;
+			add_gt(acc, u2, sr.x, (uint32_t)F_QROW); add_gt(acc, u2, sr.y, (uint32_t)F_QROW); add_gt(acc, u2, sr.z, (uint32_t)F_QROW);
+			if (n3) acc = w.qualBaseS + cur * (5u * F_QROW);                       // unknown context: the base passes through
+			uint32_t ch, q;
+			if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
+			else if (QP == 8) {
+				uint32_t qa = binIdx * (16u * F_QROW) + acc;
+				add_lt(qa, lds_u32(qa + 24), u3, 32u);
+				add_lt(qa, lds_u32(qa + 8), u3, 16u);
+				add_lt(qa, lds_u32(qa), u3, 8u);
+				q = lds_u8(qa + 4);
+				ch = lds_u8(qa + 5);
+			} else {
+				const uint32_t r16 = acc / (uint32_t)F_QROW;                       // qualBaseS == 0 here
+				q = qual_lookup<QP>(w.q, r16 >> 2, r16 & 3u, binIdx, w.B, u3);
+				ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
+			}
+			stB[c * 32] = (uint8_t)ch;
+			stB[m + 3 + c * 32] = (uint8_t)q;
+		}
 	}
 	return m;
 }
@@ -596,7 +603,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	uint8_t* s_hdr = wbase + L.w_hdr;
 	// destination of this lane's window word (cp.async), shared-window address
 	const uint32_t winS = (uint32_t)__cvta_generic_to_shared(wbase + L.w_win) + 4u * lane;
-	w.src = wbase + L.w_src; w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
+	w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
 	w.rk = P.rk;
 	w.qualBaseS = qualBaseS;
 	w.lane = lane;
