@@ -236,6 +236,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
 	P.riskyAttempt = h->d_risky.p; P.names = h->d_names.p;
 	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi; P.one = 1;
+	P.qstride = (fast && qsmem == 8) ? (uint32_t)h->dt.qualBins * 68u : 68u;   // F_QROW of gen_fast.cu
 	P.insLim = h->dt.insEnable ? h->dt.insT + 1u : 0u;
 	P.delLim = h->dt.delEnable ? h->dt.delT + 1u : 0u;
 	P.alwaysSlow = (h->dt.insEnable && h->dt.insT == 0xFFFFFFFFu) || (h->dt.delEnable && h->dt.delT == 0xFFFFFFFFu);
@@ -445,6 +446,7 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	d.delLenT = h->d_delT.p; d.delLenSym = h->d_delSym.p;
 	d.sub = h->d_sub.p; d.nSub = th.nRows * th.B;
 	d.qualT = h->d_qualT.p; d.qualSym = h->d_qualSym.p; d.qualPitch = th.qualPitch; d.nQualRows = 16 * th.B;
+	d.qualBins = ssc::fast_choose_qbins(th.B, th.RL);
 	d.qualDiagT = h->d_qualDiagT.p; d.qualDiagSym = h->d_qualDiagSym.p; d.qualDiagPitch = th.diagPitch;
 	d.compLut = th.compLut;
 	d.baseChars = (uint32_t)(uint8_t)th.baseChar[0] | ((uint32_t)(uint8_t)th.baseChar[1] << 8) |

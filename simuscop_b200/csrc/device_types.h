@@ -37,6 +37,7 @@ struct DevTables {
 	const uint32_t* delLenT; const uint16_t* delLenSym;
 	const uint4* sub; int nSub;              // rows*B per read table; table of read 2 follows when useCdf2
 	const uint32_t* qualT; const uint8_t* qualSym; int qualPitch; int nQualRows;
+	int qualBins;                            // fast kernel: bins per (ref, call) block of the shared quality image (>= B, see fast_choose_qbins)
 	const uint32_t* qualDiagT; const uint8_t* qualDiagSym; int qualDiagPitch;   // ref == call rows, [N*B][pitch]
 	uint32_t compLut;
 	uint32_t baseChars;                      // 4 ASCII characters, code i in byte i
@@ -69,6 +70,7 @@ struct GenParams {
 	uint32_t insLim, delLim;    // fast kernel: candidate tests as u < limit (0 = disabled)
 	int alwaysSlow;             // a rate of 1 (limit 2^32) sends every read down the slow path
 	uint32_t one;               // 1, opaque to the compiler (see fadd_gt in gen_fast.cu)
+	uint32_t qstride;           // fast kernel: bytes from quality row (ref, call) to (ref, call + 1): qualBins * 68 with all rows in shared memory, else 68
 	int64_t emitLo, emitHi;    // emitted-pair index range of this batch
 	const int32_t* tileStartBin;
 	int nTiles;

@@ -80,7 +80,7 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 }
 
 __host__ __device__ inline void fast_qual_bytes(const DevTables& t, int qp, int* qualBytes, int* qualSymBytes) {
-	if (qp == 8) { *qualBytes = t.nQualRows * F_QROW; *qualSymBytes = 0; }
+	if (qp == 8) { *qualBytes = 16 * t.qualBins * F_QROW; *qualSymBytes = 0; }
 	else if (qp == 2) { *qualBytes = 4 * t.B * (t.qualDiagPitch + 1) * 4; *qualSymBytes = 4 * t.B * (t.qualDiagPitch + 1); }   // odd word pitch
 	else { *qualBytes = 0; *qualSymBytes = 0; }
 }
@@ -92,6 +92,7 @@ __device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t& lo, ui
 // read-only table reads by shared-window address
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) { uint32_t v; asm("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(addr)); return v; }
 
 __device__ __forceinline__ void cp_async4(uint32_t dstShared, const void* src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dstShared), "l"(src) : "memory");
@@ -186,7 +187,7 @@ __constant__ uint32_t c_divM[10] = {0u, 0x66666667u, 0x51eb851fu, 0x10624dd3u, 0
 __constant__ uint32_t c_divS[10] = {0u, 2u, 5u, 6u, 12u, 13u, 18u, 22u, 25u, 28u};
 
 struct QualTabs {
-	const uint8_t* rows;                              // QP == 8: shared, [bin][ref*4+call] rows of F_QROW bytes
+	const uint8_t* rows; int qbins;                   // QP == 8: shared, [ref*4+call][bin (qbins per block)] rows of F_QROW bytes
 	const uint32_t* diagT; const uint8_t* diagSym;    // QP == 2: shared, ref == call rows
 	const uint32_t* gT; const uint8_t* gSym;          // full table in global memory
 	int pitch, diagPitch;
@@ -205,6 +206,7 @@ struct WarpCtx {
 	const uint32_t* rk;        // Philox round keys
 	uint32_t c0, c1;           // pair counter words
 	uint32_t qualBaseS;        // shared address folded into word 3 of the substitution rows
+	uint32_t qstride;          // bytes between the quality rows (ref, call) and (ref, call + 1) of one bin
 	int lane;
 };
 
@@ -216,7 +218,7 @@ struct WarpCtx {
 template <int QP>
 __device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur, uint32_t call, uint32_t binIdx, int B, uint32_t u3) {
 	if (QP == 8) {
-		const uint8_t* qa = q.rows + (binIdx * 16u + cur * 4u + call) * (uint32_t)F_QROW;
+		const uint8_t* qa = q.rows + ((cur * 4u + call) * (uint32_t)q.qbins + binIdx) * (uint32_t)F_QROW;
 		uint32_t k = 0;
 		add_lt(k, *(const uint32_t*)(qa + 24), u3, 32u);
 		add_lt(k, *(const uint32_t*)(qa + k + 8), u3, 16u);
@@ -384,19 +386,19 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 			const uint32_t binIdx = __umulhi((uint32_t)(j * w.B), inv);
 			const uint4 sr = w.sub[rowIdx + binIdx];
 			uint32_t acc = sr.w;
-			add_gt(acc, u2, sr.x, (uint32_t)F_QROW); add_gt(acc, u2, sr.y, (uint32_t)F_QROW); add_gt(acc, u2, sr.z, (uint32_t)F_QROW);
-			if (n3) acc = w.qualBaseS + cur * (5u * F_QROW);                       // unknown context: the base passes through
+			add_gt(acc, u2, sr.x, w.qstride); add_gt(acc, u2, sr.y, w.qstride); add_gt(acc, u2, sr.z, w.qstride);
+			if (n3) acc = w.qualBaseS + cur * (5u * w.qstride);                    // unknown context: the base passes through
 			uint32_t ch, q;
 			if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
 			else if (QP == 8) {
-				uint32_t qa = binIdx * (16u * F_QROW) + acc;
+				uint32_t qa = binIdx * (uint32_t)F_QROW + acc;
 				add_lt(qa, lds_u32(qa + 24), u3, 32u);
 				add_lt(qa, lds_u32(qa + 8), u3, 16u);
 				add_lt(qa, lds_u32(qa), u3, 8u);
-				q = lds_u8(qa + 4);
-				ch = lds_u8(qa + 5);
+				q = lds_u16(qa + 4);                                                // symbol | base character << 8
+				ch = q >> 8;
 			} else {
-				const uint32_t r16 = acc / (uint32_t)F_QROW;                       // qualBaseS == 0 here
+				const uint32_t r16 = acc / w.qstride;                              // qualBaseS == 0, qstride == F_QROW here
 				q = qual_lookup<QP>(w.q, r16 >> 2, r16 & 3u, binIdx, w.B, u3);
 				ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
 			}
@@ -533,6 +535,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	const int RL = t.RL, B = t.B;
 	// shared-window address of the quality rows, folded into the substitution rows (QP == 8)
 	const uint32_t qualBaseS = QP == 8 ? (uint32_t)__cvta_generic_to_shared(s_qual) : 0u;
+	const uint32_t qstride = P.qstride;            // QP == 8: qualBins * F_QROW, else F_QROW
 	// ---- stage the tables
 	// substitution rows: word 3 becomes the byte offset of the quality row (ref, base) inside a bin block;
 	// the three compare-adds then step it to (ref, call).  ref = last base of the context = row & 3.
@@ -541,16 +544,17 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		uint4 v = t.sub[i];
 		const int rowAll = i / B, bin = i - rowAll * B;
 		const int row = rowAll % t.nRows;
-		v.w = qualBaseS + (uint32_t)(row & 3) * (4u * F_QROW) + v.w * (uint32_t)F_QROW;
+		v.w = qualBaseS + ((uint32_t)(row & 3) * 4u + v.w) * qstride;
 		s_sub[rowAll * subPitch + bin] = v;
 	}
 	if (QP == 8) {
-		// [bin][ref*4+call][8] x {threshold, sym | char << 8}
+		// [ref*4+call][bin][8] x {threshold, sym | char << 8}: the rows one warp instruction touches (about eleven bins x
+		// four ref == call rows) spread over the banks; t.qualBins >= B pads the (ref, call) blocks for that
 #pragma unroll 1
 		for (int i = threadIdx.x; i < t.nQualRows * 8; i += FG_THREADS) {
 			const int r = i >> 3, k = i & 7;
 			const int rc = r / B, bin = r - rc * B;
-			uint32_t* dst = (uint32_t*)(s_qual + (bin * 16 + rc) * F_QROW + k * 8);
+			uint32_t* dst = (uint32_t*)(s_qual + (rc * t.qualBins + bin) * F_QROW + k * 8);
 			dst[0] = t.qualT[i];
 			dst[1] = (uint32_t)t.qualSym[i] | (((t.baseChars >> (8 * (rc & 3))) & 0xffu) << 8);
 		}
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	WarpCtx w;
 	w.B = t.B; w.subPitch = subPitch; w.minQ = t.minQ; w.RL = t.RL; w.nInsLen = t.nInsLen; w.nDelLen = t.nDelLen;
 	w.nBasesM1 = t.N - 1; w.mDelta = 0; w.baseChars = t.baseChars; w.compLut = t.compLut;
-	w.q.rows = s_qual; w.q.diagT = (const uint32_t*)s_qual; w.q.diagSym = s_qualSym;
+	w.q.rows = s_qual; w.q.qbins = t.qualBins; w.q.diagT = (const uint32_t*)s_qual; w.q.diagSym = s_qualSym;
 	w.q.gT = t.qualT; w.q.gSym = t.qualSym; w.q.pitch = t.qualPitch; w.q.diagPitch = t.qualDiagPitch;
 	w.insT = s_insT; w.insSym = s_insSym; w.delT = s_delT; w.delSym = s_delSym;
 	w.win = (const uint32_t*)(wbase + L.w_win);
@@ -605,18 +609,18 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	const uint32_t winS = (uint32_t)__cvta_generic_to_shared(wbase + L.w_win) + 4u * lane;
 	w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
 	w.rk = P.rk;
-	w.qualBaseS = qualBaseS;
+	w.qualBaseS = qualBaseS; w.qstride = qstride;
 	w.lane = lane;
 
 	// ---- per-lane constants
 	// bin of output position j = j*B/RL (Profile.cpp:1671) for an indel-free read, as the byte offset of that bin's
 	// substitution row entry; lanes past the read end (last chunk only) are clamped so that every table index stays valid
-	uint32_t subBinOff[NCH];
+	uint32_t binOf[NCH];
 #pragma unroll
 	for (int c = 0; c < NCH; c++) {
 		int j = c * 32 + lane;
 		if (j > RL - 1) j = RL - 1;
-		subBinOff[c] = (uint32_t)((j * B) / RL) * 16u;
+		binOf[c] = (uint32_t)((j * B) / RL);
 	}
 	// insertion / deletion candidate tests as "u < limit" (0 = disabled); a limit of 2^32 forces the slow path
 	// (P.insLim / P.delLim / P.alwaysSlow, computed by the host, are constant-bank operands: no registers)
@@ -799,23 +803,23 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 					for (int c = 0; c < NCH; c++) {
 						const uint32_t v6 = __funnelshift_r(dptr[c * dstep], dptr[c * dstep + 1], dsh) & 63u;
 						const uint32_t rowIdx = *(const uint16_t*)((c == 0 ? lut0 : lutN) + v6 * 2u);
-						const uint4 sr = *(const uint4*)(subMB + rowIdx * 16u + subBinOff[c]);
+						const uint4 sr = *(const uint4*)(subMB + (rowIdx + binOf[c]) * 16u);
 						uint32_t acc = sr.w;
-						fadd_gt(acc, x2[c], sr.x, (uint32_t)F_QROW, one);
-						fadd_gt(acc, x2[c], sr.y, (uint32_t)F_QROW, one);
-						fadd_gt(acc, x2[c], sr.z, (uint32_t)F_QROW, one);
+						fadd_gt(acc, x2[c], sr.x, P.qstride, one);
+						fadd_gt(acc, x2[c], sr.y, P.qstride, one);
+						fadd_gt(acc, x2[c], sr.z, P.qstride, one);
 						uint32_t ch, q;
 						if (QP == 8) {
-							uint32_t qa = subBinOff[c] * (uint32_t)F_QROW + acc;     // shared address of row (bin, ref, call)
+							uint32_t qa = binOf[c] * (uint32_t)F_QROW + acc;         // shared address of row (ref, call, bin)
 							fadd_lt(qa, lds_u32(qa + 24), x3[c], 32u, one);
 							fadd_lt(qa, lds_u32(qa + 8), x3[c], 16u, one);
 							fadd_lt(qa, lds_u32(qa), x3[c], 8u, one);
-							q = lds_u8(qa + 4);
-							ch = lds_u8(qa + 5);
+							q = lds_u16(qa + 4);                                     // symbol | base character << 8
+							ch = q >> 8;
 						} else {
 							const uint32_t r16 = acc / (uint32_t)F_QROW;             // qualBaseS == 0 here
 							const uint32_t call = r16 & 3u;
-							q = qual_lookup<QP>(w.q, r16 >> 2, call, subBinOff[c] >> 4, B, x3[c]);
+							q = qual_lookup<QP>(w.q, r16 >> 2, call, binOf[c], B, x3[c]);
 							ch = __byte_perm(baseChars, 0, 0x4440u | call);
 						}
 						if (c < NCH - 1) {
@@ -863,6 +867,38 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		}
 	}
 
+}
+
+// Bins per (ref, call) block of the shared-memory quality image.  The three probes of a quality search are one word per
+// lane at row (ref, call, bin); the 32 lanes of a warp instruction cover about RL/32 consecutive bins and mostly the four
+// ref == call rows.  The candidate in [B, B + 8) with the fewest bank conflicts on a deterministic sample of such access
+// patterns wins (bin-major rows, the first layout, cost 4.7 wavefronts per probe; this one about 2).
+int fast_choose_qbins(int B, int RL) {
+	int best = B; long bestScore = -1;
+	for (int qb = B; qb < B + 8; qb++) {
+		long score = 0;
+		uint32_t lcg = 12345u;
+		for (int trial = 0; trial < 64; trial++) {
+			for (int c = 0; c * 32 < RL; c++) {
+				int nAddr[32] = {0}; int addr[32][32];
+				for (int lane = 0; lane < 32; lane++) {
+					int j = c * 32 + lane; if (j > RL - 1) j = RL - 1;
+					lcg = lcg * 1664525u + 1013904223u;
+					const int ref = (int)(lcg >> 30);
+					const int word = ((ref * 5) * qb + (j * B) / RL) * (F_QROW / 4) + 6;
+					int* a = addr[word & 31]; int& n = nAddr[word & 31];
+					bool seen = false;
+					for (int i = 0; i < n; i++) seen |= a[i] == word;
+					if (!seen) a[n++] = word;
+				}
+				int worst = 0;
+				for (int b = 0; b < 32; b++) worst = nAddr[b] > worst ? nAddr[b] : worst;
+				score += worst;
+			}
+		}
+		if (bestScore < 0 || score < bestScore) { bestScore = score; best = qb; }
+	}
+	return best;
 }
 
 bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemBytes) {

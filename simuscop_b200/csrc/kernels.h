@@ -35,6 +35,7 @@ struct GenVariant {
 GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit);
 cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, cudaStream_t stream);
 bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemBytes);   // qmode: 8 / 2 / 0, see gen_fast.cu
+int fast_choose_qbins(int B, int RL);
 cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
                                  cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool pass2);
 cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream);
