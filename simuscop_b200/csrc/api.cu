@@ -68,6 +68,7 @@ struct ssc_handle {
 	int64_t batchPairs = 1 << 20;
 	bool fp64 = false;
 	bool forceGeneric = false;
+	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
 	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
 	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
@@ -214,7 +215,8 @@ int build_gz_tables(ssc_handle* h, const ssc::GenParams& P, int nTiles) {
 	ssc::GzTables tab;
 	const char* err = ssc::gz_build_tables(hist, &tab);
 	if (err[0]) return fail(SSC_ERR_INVALID, "gzip tables: %s", err);
-	CK(cudaMemcpy(h->d_gzTab, &tab, sizeof(tab), cudaMemcpyHostToDevice));
+	CK(cudaMemcpyAsync(h->d_gzTab, &tab, sizeof(tab), cudaMemcpyHostToDevice, h->compute));   // stream order with the deflate kernel
+	CK(cudaStreamSynchronize(h->compute));          // tab lives on this stack frame
 	h->haveGz = true;
 	return SSC_OK;
 }
@@ -235,7 +237,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	P.hap2 = h->d_hap2.p; P.hapN = h->d_hapN.p;
 	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
 	P.riskyAttempt = h->d_risky.p; P.names = h->d_names.p;
-	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi; P.one = 1;
+	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi; P.one = 1; P.noSplice = h->noSplice ? 1 : 0;
 	P.qstride = (fast && qsmem == 8) ? (uint32_t)h->dt.qualBins * 68u : 68u;   // F_QROW of gen_fast.cu
 	P.insLim = h->dt.insEnable ? h->dt.insT + 1u : 0u;
 	P.delLim = h->dt.delEnable ? h->dt.delT + 1u : 0u;
@@ -395,6 +397,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 	}
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
 	if (!strcmp(key, "max_ctas")) { if (value < 0) return fail(SSC_ERR_INVALID, "max_ctas must be >= 0"); h->maxCtas = (int)value; return SSC_OK; }
+	if (!strcmp(key, "no_splice")) { h->noSplice = value != 0; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
 	if (!strcmp(key, "fp64_search")) {
 		if (h->havePlan) return fail(SSC_ERR_STATE, "fp64_search must be set before ssc_set_plan");
@@ -510,7 +513,10 @@ int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n) {
 	CK(cudaSetDevice(h->device));
 	if (h->d_ref.n < n) CK(h->d_ref.alloc((size_t)n + (size_t)n / 8 + 4096));
 	CK(cudaStreamSynchronize(h->compute));          // earlier ssc_genome_append_ref launches still read the old reference
-	if (n) CK(cudaMemcpy(h->d_ref.p, ascii, (size_t)n, cudaMemcpyHostToDevice));
+	// in stream order with the pack kernels that read it: a plain cudaMemcpy from pageable memory runs on the legacy stream,
+	// which the (non-blocking) compute stream does not wait for, and may return before the DMA has landed
+	if (n) CK(cudaMemcpyAsync(h->d_ref.p, ascii, (size_t)n, cudaMemcpyHostToDevice, h->compute));
+	CK(cudaStreamSynchronize(h->compute));          // the caller may free the chromosome string
 	h->refSize = n;
 	h->stats.h2d_bytes += n;
 	return SSC_OK;

@@ -69,6 +69,7 @@ struct GenParams {
 	uint32_t rk[20];            // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
 	uint32_t insLim, delLim;    // fast kernel: candidate tests as u < limit (0 = disabled)
 	int alwaysSlow;             // a rate of 1 (limit 2^32) sends every read down the slow path
+	int noSplice;               // tests: reads with indel events always take the position-by-position path (emit_mapped)
 	uint32_t one;               // 1, opaque to the compiler (see fadd_gt in gen_fast.cu)
 	uint32_t qstride;           // fast kernel: bytes from quality row (ref, call) to (ref, call + 1): qualBins * 68 with all rows in shared memory, else 68
 	int64_t emitLo, emitHi;    // emitted-pair index range of this batch

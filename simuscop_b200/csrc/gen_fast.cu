@@ -51,7 +51,7 @@ static constexpr int F_LUT_N = 6 * 64;          // context LUT (16-bit entries: 
 
 struct FastLayout {
 	int sub, qual, qualSym, isizeT, isizeSym, insT, insSym, delT, delSym, lut, dig, warp, total;
-	int w_ev, w_insb, w_win, w_hdr, perWarp;
+	int w_ev, w_insb, w_insp, w_out, w_win, w_hdr, perWarp;
 };
 
 __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
@@ -71,6 +71,8 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 	int w = 0;
 	L.w_ev = w; w += F_EV_MAX * 8;
 	L.w_insb = w; w += F_INS_CAP;
+	L.w_insp = w; w += 48;                          // inserted bases, packed: one pad word in front, 8 + 1 words
+	L.w_out = w; w += 80;                           // spliced (post-indel) read, packed like a window: one pad word in front, 16 + 1 words
 	L.w_win = w; w += 2 * F_WIN_WORDS * 4;          // one window per mate, filled by cp.async
 	L.w_hdr = w; w += 96;                           // record header of the current pair
 	L.perWarp = w;
@@ -203,6 +205,7 @@ struct WarpCtx {
 	const uint32_t* win;       // shared window: data words [0..16), mask words [16..25)
 	const uint8_t* lutB;       // shared: context LUT (16-bit entries, 6 variants of 64)
 	uint32_t* ev; uint8_t* insb;
+	uint32_t* insp; uint32_t* outw;   // packed inserted bases / spliced read (word 0 of each array, a pad word lies in front)
 	const uint32_t* rk;        // Philox round keys
 	uint32_t c0, c1;           // pair counter words
 	uint32_t qualBaseS;        // shared address folded into word 3 of the substitution rows
@@ -267,19 +270,22 @@ __device__ __forceinline__ int coop_lookup(const uint32_t* T, const uint16_t* sy
 }
 
 // Slow path of Profile::predict (a read with an indel candidate or a non-ACGT base): compact, not unrolled.
+// Step 1, scan_events: the indel events of the read (Profile.cpp:1610-1634) as a sorted list of output-coordinate
+//   segments {first output position behind the event's template base, inserted bases, template shift behind it}.
+// Step 2a, splice_read + emit_packed (no non-ACGT base near the read, post-indel length within the NCH chunks): the
+//   post-indel source sequence (Profile.cpp:1636-1658) is assembled 16 bases per lane from the packed window with funnel
+//   shifts, in store orientation, and the per-base work is the fast path's (context cut out of packed words).
+// Step 2b, emit_mapped (everything else): every lane maps its output position to a template base of the window (or an
+//   inserted base) and gets the two context bases from its neighbours by shuffle.
+struct IndelPlan {
+	uint2 e0;          // first event (the others are in w.ev[1..])
+	int nEv, m, insTotal;
+};
+
 // evbits: per lane, bit 2c = insertion test hit at cycle 32c+lane, bit 2c+1 = deletion test hit.
-// x2/x3: the substitution / quality draws of output positions 32c+lane, c < NCH (registers of the caller).
-// The post-indel source sequence (Profile.cpp:1636-1658) is never materialised: the events are kept as a sorted list of
-// output-coordinate segments {first output position, inserted bases, template shift behind it}; every lane maps its
-// output position to a template base of the packed window (or an inserted base) and gets the two context bases from its
-// neighbours by shuffle.  Writes bases/quals into stage[H ..]; returns m.
-template <int NCH, int QP>
-__device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int mate, bool rev, int relFirst,
-                                      uint8_t* stage, int H, unsigned int* errorFlags,
-                                      const uint32_t (&x2)[NCH], const uint32_t (&x3)[NCH]) {
+__device__ __forceinline__ IndelPlan scan_events(const WarpCtx& w, uint32_t evbits, int mate, unsigned int* errorFlags) {
 	const int RL = w.RL, lane = w.lane;
 	const int chunksRL = (RL + 31) >> 5;
-	const uint32_t c2cyc = ((uint32_t)mate << 28) | ((uint32_t)STREAM_CYCLE << 24);
 	const uint32_t c2len = ((uint32_t)mate << 28) | ((uint32_t)STREAM_LEN << 24);
 	const uint32_t c2ins = ((uint32_t)mate << 28) | ((uint32_t)STREAM_INSBASE << 24);
 	// event k: x = first output position behind the event's template base | inserted bases << 9 | their offset in insb << 17,
@@ -331,6 +337,122 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 		nEv = 0; m = RL;
 	}
 	__syncwarp();
+	IndelPlan pl;
+	pl.e0 = e0; pl.nEv = nEv; pl.m = m; pl.insTotal = nEv ? insTotal : 0;
+	return pl;
+}
+
+// Step 2a.  A packed array holds base i in bits 2*(i & 15) of word i >> 4.  gather16: the 16 bases src[q .. q+16) of such an
+// array, restricted to the positions [lo, hi) of the word (0 <= lo < hi <= 16); q + lo >= 0 (q itself may be negative: the
+// arrays have a pad word in front).
+__device__ __forceinline__ uint32_t gather16(const uint32_t* src, int q, int lo, int hi) {
+	const int wi = q >> 4;
+	const uint32_t f = __funnelshift_r(src[wi], src[wi + 1], (uint32_t)(q & 15) * 2u);
+	return f & (0xffffffffu >> (32 - 2 * hi)) & (0xffffffffu << (2 * lo));
+}
+
+// The post-indel read in store orientation (forward reads: output order; reverse reads: reversed, template and inserted
+// bases as the store holds them, i.e. complemented), base y at packed index dOff + y of w.outw -- exactly what the
+// window holds for an indel-free read of length m, so that the fast path's context extraction applies unchanged.
+// Lane L < 16 assembles word L from the template runs between the events (slices of the window) and the inserted runs.
+__device__ __forceinline__ void splice_read(const WarpCtx& w, const IndelPlan& pl, bool rev, int dOff) {
+	const int RL = w.RL, lane = w.lane, m = pl.m, insTotal = pl.insTotal;
+	const uint2* evs = (const uint2*)w.ev;
+	// inserted bases, packed in store orientation
+	if (lane < 9) w.insp[lane] = 0u;
+	__syncwarp();
+	for (int i = lane; i < insTotal; i += 32) {
+		uint32_t code = w.insb[rev ? insTotal - 1 - i : i];
+		if (rev) code = (w.compLut >> (2 * code)) & 3u;
+		atomicOr(&w.insp[i >> 4], code << ((i & 15) * 2));
+	}
+	__syncwarp();
+	const int y0 = 16 * lane - dOff;                   // store-order index of the first base of this lane's word
+	uint32_t word = 0;
+	int prevO = 0, prevShift = 0;
+#pragma unroll 1
+	for (int k = 0; k <= pl.nEv; k++) {
+		int start = m, nIns = 0, insOff = 0, shiftAfter = 0;
+		if (k < pl.nEv) {
+			const uint2 e = k == 0 ? pl.e0 : evs[k];
+			start = (int)(e.x & 0x1ffu); nIns = (int)((e.x >> 9) & 0xffu); insOff = (int)(e.x >> 17); shiftAfter = (int)e.y;
+		}
+		// template run: output [prevO, start) <- template [prevO - prevShift, start - prevShift)
+		{
+			const int n = start - prevO, t1 = prevO - prevShift;
+			const int dst = rev ? m - start : prevO;
+			const int src = rev ? RL - (t1 + n) : t1;
+			const int lo = max(dst, y0) - y0, hi = min(dst + n, y0 + 16) - y0;
+			if (lo < hi) word |= gather16(w.win, dOff + src + y0 - dst, lo, hi);
+		}
+		if (nIns > 0) {
+			const int dst = rev ? m - (start + nIns) : start;
+			const int src = rev ? insTotal - (insOff + nIns) : insOff;
+			const int lo = max(dst, y0) - y0, hi = min(dst + nIns, y0 + 16) - y0;
+			if (lo < hi) word |= gather16(w.insp, src + y0 - dst, lo, hi);
+		}
+		prevO = start + nIns; prevShift = shiftAfter;
+	}
+	if (lane < 16) w.outw[lane] = word;
+	__syncwarp();
+}
+
+// Per-base work of a read of m <= 32 * NCH bases whose source sequence is packed at index dOff (store orientation) of
+// win: the fast path's phase C with the position bins of the post-indel length (Profile.cpp:1671), rolled.
+template <int NCH, int QP>
+__device__ __forceinline__ void emit_packed(const WarpCtx& w, const uint32_t* win, int dOff, bool rev, int m, uint32_t lut0, uint32_t lutN,
+                                            uint8_t* stage, int H, const uint32_t (&x2)[NCH], const uint32_t (&x3)[NCH]) {
+	const int lane = w.lane;
+	const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
+	const int chunksM = (m + 31) >> 5;
+	uint8_t* const stB = stage + H + lane;
+	uint32_t a2[NCH], a3[NCH];
+#pragma unroll
+	for (int k = 0; k < NCH; k++) { a2[k] = x2[k]; a3[k] = x3[k]; }
+#pragma unroll 1
+	for (int c = 0; c < chunksM; c++) {
+		const int j = c * 32 + lane;
+		const uint32_t u2 = a2[0], u3 = a3[0];
+#pragma unroll
+		for (int k = 0; k + 1 < NCH; k++) { a2[k] = a2[k + 1]; a3[k] = a3[k + 1]; }
+		const int jc = j < m ? j : m - 1;                // lanes past the read end: any valid index
+		// forward: the three bases of cycles (j-2, j-1, j) start at index dOff + j - 2; reverse: cycles (j, j-1, j-2) at dOff + m-1 - j
+		const int rel = rev ? dOff + m - 1 - jc : dOff + jc - 2;
+		const uint32_t v6 = __funnelshift_r(win[rel >> 4], win[(rel >> 4) + 1], (uint32_t)(rel & 15) * 2u) & 63u;
+		const uint32_t rowIdx = *(const uint16_t*)(w.lutB + (c == 0 ? lut0 : lutN) + v6 * 2u);
+		const uint32_t binIdx = __umulhi((uint32_t)(jc * w.B), inv);
+		const uint4 sr = w.sub[rowIdx + binIdx];
+		uint32_t acc = sr.w;
+		add_gt(acc, u2, sr.x, w.qstride); add_gt(acc, u2, sr.y, w.qstride); add_gt(acc, u2, sr.z, w.qstride);
+		uint32_t ch, q;
+		if (QP == 8) {
+			uint32_t qa = binIdx * (uint32_t)F_QROW + acc;
+			add_lt(qa, lds_u32(qa + 24), u3, 32u);
+			add_lt(qa, lds_u32(qa + 8), u3, 16u);
+			add_lt(qa, lds_u32(qa), u3, 8u);
+			q = lds_u16(qa + 4);                                                // symbol | base character << 8
+			ch = q >> 8;
+		} else {
+			const uint32_t r16 = acc / w.qstride;                              // qualBaseS == 0, qstride == F_QROW here
+			q = qual_lookup<QP>(w.q, r16 >> 2, r16 & 3u, binIdx, w.B, u3);
+			ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
+		}
+		if (j < m) {
+			stB[c * 32] = (uint8_t)ch;
+			stB[m + 3 + c * 32] = (uint8_t)q;
+		}
+	}
+}
+
+// Step 2b.  x2/x3: the substitution / quality draws of output positions 32c+lane, c < NCH (registers of the caller).
+// Writes bases/quals into stage[H ..].
+template <int NCH, int QP>
+__device__ __forceinline__ void emit_mapped(const WarpCtx& w, const IndelPlan& pl, int mate, bool rev, int relFirst,
+                                            uint8_t* stage, int H, const uint32_t (&x2)[NCH], const uint32_t (&x3)[NCH]) {
+	const int RL = w.RL, lane = w.lane, m = pl.m, nEv = pl.nEv;
+	const uint2 e0 = pl.e0;
+	const uint2* evs = (const uint2*)w.ev;
+	const uint32_t c2cyc = ((uint32_t)mate << 28) | ((uint32_t)STREAM_CYCLE << 24);
 	const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
 	const int chunksM = (m + 31) >> 5;
 	uint32_t prev = 0;                               // codes of the previous chunk ('X' pads in front of the read: code 0, no flag)
@@ -406,7 +528,6 @@ __device__ __forceinline__ int slow_read(const WarpCtx& w, uint32_t evbits, int 
 			stB[m + 3 + c * 32] = (uint8_t)q;
 		}
 	}
-	return m;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -608,6 +729,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	// destination of this lane's window word (cp.async), shared-window address
 	const uint32_t winS = (uint32_t)__cvta_generic_to_shared(wbase + L.w_win) + 4u * lane;
 	w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
+	w.insp = (uint32_t*)(wbase + L.w_insp) + 1; w.outw = (uint32_t*)(wbase + L.w_out) + 1;
 	w.rk = P.rk;
 	w.qualBaseS = qualBaseS; w.qstride = qstride;
 	w.lane = lane;
@@ -846,8 +968,17 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 						if (c == NCH - 1 && jLast >= RL) hit = 0;
 						evbits |= hit << (2 * c);
 					}
-					const int relFirst = rev ? (dOff + RL - 1) : dOff;
-					m = slow_read<NCH, QP>(w, evbits, mate, rev, relFirst, stage, H, &P.result->errorFlags, x2, x3);
+					const IndelPlan pl = scan_events(w, evbits, mate, &P.result->errorFlags);
+					m = pl.m;
+					// a non-ACGT base in the window, or a read that outgrew the NCH chunks of draws: position-by-position path
+					const bool hasN = __any_sync(0xffffffffu, lane >= 16 && lane < 25 && s_win[lane] != 0u);
+					if (hasN || m > 32 * NCH || P.noSplice) {
+						const int relFirst = rev ? (dOff + RL - 1) : dOff;
+						emit_mapped<NCH, QP>(w, pl, mate, rev, relFirst, stage, H, x2, x3);
+					} else {
+						if (pl.nEv) splice_read(w, pl, rev, dOff);
+						emit_packed<NCH, QP>(w, pl.nEv ? w.outw : s_win, dOff, rev, m, rev ? lutRev0 : lutFwd0, rev ? 128u : 0u, stage, H, x2, x3);
+					}
 					if (lane == 0) { stage[H + m] = '\n'; stage[H + m + 1] = '+'; stage[H + m + 2] = '\n'; stage[H + 2 * m + 3] = '\n'; }
 				}
 				if (mate == 0) pos1 += (uint32_t)(H + 2 * m + 4); else pos2 += (uint32_t)(H + 2 * m + 4);

@@ -32,7 +32,7 @@ def test_fastq_bit_exact_vs_instrumented_reference(name, gen, workdir):
         assert len(r1) > 0
 
 
-@pytest.mark.parametrize("mode", ["force_generic", "fp64_search"])
+@pytest.mark.parametrize("mode", ["force_generic", "fp64_search", "no_splice"])
 @pytest.mark.parametrize("name", ["pe_xten", "pe_tiny", "se_gaiix"])
 def test_fallback_kernels_bit_exact(name, mode, built, workdir):
     """The generic integer kernel and the FP64 linear-search ground-truth kernel give the same bytes."""
@@ -149,7 +149,7 @@ def test_synthetic_profiles_cli_and_abi(name, built, workdir):
     assert len(r1) > 10000
     o1, o2, _ = oracle_binding.generate(plan, scn["seed"])
     assert (o1, o2) == (r1, r2)
-    for opt in (None, "force_generic"):
+    for opt in (None, "force_generic", "no_splice"):
         g = cuda_binding.Generator(0)
         try:
             if opt:
@@ -176,7 +176,7 @@ def test_reads_beyond_the_scratch_limits_fail_loudly(built, workdir):
     scn = helpers.build_stress("overflow", workdir)
     plans, out_ref = helpers.run_reference_philox(scn, tag="ov")
     plan = planfile.read_plan(plans[0])
-    for opt in (None, "force_generic"):
+    for opt in (None, "force_generic", "no_splice"):
         g = cuda_binding.Generator(0)
         try:
             if opt:
