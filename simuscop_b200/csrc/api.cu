@@ -151,6 +151,14 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 		cap = (uint64_t)pairs * (uint64_t)h->maxRecBytes + 4096;
 	}
 	int nFiles = h->dt.paired ? 2 : 1;
+	{
+		// the fast kernel addresses its blob scratch (FG_SLOT bytes per record, both files) with 32-bit offsets
+		const int64_t maxFast = (int64_t)(((1ull << 32) - (1ull << 20)) / ((uint64_t)FG_SLOT * (uint64_t)nFiles));
+		if (pairs > maxFast) {
+			pairs = (maxFast / GEN_TILE_PAIRS) * GEN_TILE_PAIRS;
+			cap = (uint64_t)pairs * (uint64_t)h->maxRecBytes + 4096;
+		}
+	}
 	if (pairs != h->slabPairs || cap != h->slabCap) {
 		for (int b = 0; b < 2; b++)
 			for (int f = 0; f < 2; f++) {
@@ -158,9 +166,12 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 				if (h->h_out[b][f]) cudaFreeHost(h->h_out[b][f]);
 				h->d_out[b][f] = nullptr; h->h_out[b][f] = nullptr;
 			}
-		for (int f = 0; f < 2; f++) { if (h->d_slots[f]) cudaFree(h->d_slots[f]); h->d_slots[f] = nullptr; }
+		if (h->d_slots[0]) cudaFree(h->d_slots[0]);
+		h->d_slots[0] = h->d_slots[1] = nullptr;
 		h->slabPairs = pairs; h->slabCap = cap;
-		for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_slots[f], (size_t)pairs * FG_SLOT + 64));
+		// one scratch: the two blobs of a ticket lie side by side (the kernel addresses both from one base pointer)
+		CK(cudaMalloc((void**)&h->d_slots[0], (size_t)pairs * FG_SLOT * nFiles + (size_t)FG_CHUNK * FG_SLOT + 64));
+		h->d_slots[1] = nFiles == 2 ? h->d_slots[0] + (size_t)FG_CHUNK * FG_SLOT : nullptr;
 		for (int f = 0; f < 2; f++) { if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]); h->d_gzBlobs[f] = nullptr; }
 		CK(h->d_ticket2.alloc(1));
 		CK(h->d_blobPrefix.alloc((size_t)(pairs / 16) + 2));
@@ -197,7 +208,7 @@ int64_t emit_index_of_plan(const ssc_handle* h, int64_t p) {
 // Fits the gzip Huffman table of a plan to the first tickets of its first batch (the blobs are in scratch already).
 int build_gz_tables(ssc_handle* h, const ssc::GenParams& P, int nTiles) {
 	const int sample = std::min(nTiles, 256);
-	const size_t pitch = (size_t)FG_CHUNK * FG_SLOT;
+	const size_t pitch = P.blobPitch;
 	std::vector<unsigned long long> lens((size_t)sample);
 	std::vector<uint8_t> blob((size_t)sample * pitch);
 	uint64_t hist[256];
@@ -258,6 +269,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
+		P.blobPitch = (uint32_t)(FG_CHUNK * FG_SLOT) * (h->dt.paired ? 2u : 1u);
 		cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 		if (h->timeKernels) {
 			while ((int)h->kev.size() < h->kevUsed + 3) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }
@@ -272,10 +284,10 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, nullptr, false));
 			if (!h->haveGz) { int rc = build_gz_tables(h, P, nTiles); if (rc) return rc; }
 			CK(cudaMemsetAsync(h->d_gzLens.p, 0, sizeof(unsigned long long) * nTiles, s));
-			CK(ssc::launch_deflate_blobs(P.out1, P.out2, P.tileState, nTiles, FG_CHUNK * FG_SLOT, h->d_gzBlobs[0], h->d_gzBlobs[1], h->d_gzLens.p,
+			CK(ssc::launch_deflate_blobs(P.out1, P.out2, P.tileState, nTiles, P.blobPitch, h->d_gzBlobs[0], h->d_gzBlobs[1], h->d_gzLens.p,
 			                             FG_CHUNK * FG_SLOT, h->d_gzTab, &P.result->errorFlags, h->smCount, s));
 			ssc::GenParams P2 = P;
-			P2.out1 = h->d_gzBlobs[0]; P2.out2 = h->d_gzBlobs[1]; P2.tileState = h->d_gzLens.p;
+			P2.out1 = h->d_gzBlobs[0]; P2.out2 = h->d_gzBlobs[1]; P2.tileState = h->d_gzLens.p; P2.blobPitch = FG_CHUNK * FG_SLOT;
 			CK(ssc::launch_pass2(P2, h->smCount, s));
 			if (e2) CK(cudaEventRecord(e2, s));
 			h->stats.launches += 3;
@@ -358,7 +370,7 @@ int ssc_destroy(ssc_handle* h) {
 		}
 		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
 		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
-		if (h->d_slots[b]) cudaFree(h->d_slots[b]);
+		if (b == 0 && h->d_slots[0]) cudaFree(h->d_slots[0]);   // d_slots[1] points into the same allocation
 		if (h->d_result[b]) cudaFree(h->d_result[b]);
 		if (h->h_result[b]) cudaFreeHost(h->h_result[b]);
 		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();

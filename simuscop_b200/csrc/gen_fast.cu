@@ -285,7 +285,6 @@ struct IndelPlan {
 // evbits: per lane, bit 2c = insertion test hit at cycle 32c+lane, bit 2c+1 = deletion test hit.
 __device__ __forceinline__ IndelPlan scan_events(const WarpCtx& w, uint32_t evbits, int mate, unsigned int* errorFlags) {
 	const int RL = w.RL, lane = w.lane;
-	const int chunksRL = (RL + 31) >> 5;
 	const uint32_t c2len = ((uint32_t)mate << 28) | ((uint32_t)STREAM_LEN << 24);
 	const uint32_t c2ins = ((uint32_t)mate << 28) | ((uint32_t)STREAM_INSBASE << 24);
 	// event k: x = first output position behind the event's template base | inserted bases << 9 | their offset in insb << 17,
@@ -294,7 +293,12 @@ __device__ __forceinline__ IndelPlan scan_events(const WarpCtx& w, uint32_t evbi
 	uint2 e0 = make_uint2(0u, 0u);
 	int nEv = 0, insTotal = 0, cum = 0, skipUntil = 0;
 	bool tooMany = false;
-	for (int c = 0; c < chunksRL; c++) {
+	// chunks with a candidate in any lane (REDUX.OR over the warp): bit 2c
+	const uint32_t anyBits = __reduce_or_sync(0xffffffffu, evbits);
+	uint32_t chunkBits = (anyBits | (anyBits >> 1)) & 0x55555555u;
+	while (chunkBits) {
+		const int c = (__ffs(chunkBits) - 1) >> 1;
+		chunkBits &= chunkBits - 1;
 		const uint32_t insMask = __ballot_sync(0xffffffffu, (evbits >> (2 * c)) & 1u);
 		const uint32_t delMask = __ballot_sync(0xffffffffu, (evbits >> (2 * c + 1)) & 1u);
 		uint32_t mask = insMask | delMask;
@@ -619,7 +623,7 @@ __global__ void __launch_bounds__(CP_THREADS) move_blobs_kernel(const GenParams 
 		const unsigned long long d1 = excl >> 31, d2 = excl & 0x7fffffffull;
 		const int l1 = (int)(mine >> 31), l2 = (int)(mine & 0x7fffffffull);
 		if (d1 + (unsigned)l1 > P.cap1 || d2 + (unsigned)l2 > P.cap2) continue;   // flagged by the scan
-		const size_t blob = (size_t)j * (FG_CHUNK * FG_SLOT);
+		const size_t blob = (size_t)j * P.blobPitch;
 		copy_realign(P.out1 + blob, l1, P.dense1 + d1, lane);
 		if (l2) copy_realign(P.out2 + blob, l2, P.dense2 + d2, lane);
 	}
@@ -770,7 +774,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		const uint32_t nSlots = (uint32_t)(P.emitHi - P.emitLo);
 		const int count = (int)(slot0 + FG_CHUNK < nSlots ? FG_CHUNK : nSlots - slot0);
 		uint32_t acc = 0;                                // bases | haplotype bytes << 16 of this ticket
-		uint32_t pos1 = (uint32_t)chunk * (FG_CHUNK * FG_SLOT), pos2 = pos1;   // next free byte of this ticket's blobs (scratch < 2^32 bytes)
+		// next free byte of this ticket's two blobs, relative to P.out1 (file 2's blob follows file 1's; scratch < 2^32 bytes).
+		// posA belongs to the file of the current mate: the two cursors change places after every mate of a pair.
+		const uint32_t blobBase = (uint32_t)chunk * P.blobPitch;
+		uint32_t posA = blobBase, posB = blobBase + (uint32_t)(FG_CHUNK * FG_SLOT);
 
 		// ---- ticket prologue, lane-parallel: lane L prepares pair slot0 + L (bin, pair ID, fragment draw, header digit counts);
 		// the pair loop below fetches these by shuffle instead of every lane repeating the same scalar work for every pair
@@ -884,7 +891,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				w.win = s_win;
 				w.mDelta = mOff - dOff;
 				const uint32_t c2cyc = ((uint32_t)mate << 28) | ((uint32_t)STREAM_CYCLE << 24);
-				uint8_t* stage = mate == 0 ? P.out1 + pos1 : P.out2 + pos2;
+				uint8_t* stage = P.out1 + posA;
 				const uint4* subM = s_sub + ((mate == 1 && t.useCdf2) ? t.nRows * subPitch : 0);
 				w.sub = subM;
 
@@ -962,11 +969,11 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 					uint32_t evbits = 0;
 #pragma unroll
 					for (int c = 0; c < NCH; c++) {
-						const bool ins = t.insEnable && x0[c] <= t.insT;                 // p <= insertRate, Profile.cpp:1560-1561
-						const bool del = !ins && t.delEnable && x1[c] <= t.delT;         // p2 < delRate/(1-insertRate), :1569-1570
-						uint32_t hit = (ins ? 1u : 0u) | (del ? 2u : 0u);
-						if (c == NCH - 1 && jLast >= RL) hit = 0;
-						evbits |= hit << (2 * c);
+						const bool valid = c < NCH - 1 || jLast < RL;
+						const bool ins = valid && t.insEnable && x0[c] <= t.insT;        // p <= insertRate, Profile.cpp:1560-1561
+						const bool del = valid && t.delEnable && x1[c] <= t.delT;        // p2 < delRate/(1-insertRate), :1569-1570
+						if (ins) evbits |= 1u << (2 * c);
+						else if (del) evbits |= 2u << (2 * c);
 					}
 					const IndelPlan pl = scan_events(w, evbits, mate, &P.result->errorFlags);
 					m = pl.m;
@@ -981,19 +988,21 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 					}
 					if (lane == 0) { stage[H + m] = '\n'; stage[H + m + 1] = '+'; stage[H + m + 2] = '\n'; stage[H + 2 * m + 3] = '\n'; }
 				}
-				if (mate == 0) pos1 += (uint32_t)(H + 2 * m + 4); else pos2 += (uint32_t)(H + 2 * m + 4);
+				posA += (uint32_t)(H + 2 * m + 4);
+				if (nMates == 2) { const uint32_t tswap = posA; posA = posB; posB = tswap; }
 				acc += (uint32_t)m;                                                    // bases of the ticket (<= 2^14)
 				__syncwarp();
 			}
 		}
 		{
-			const uint32_t ticket = (uint32_t)chunk, blobBase = ticket * (FG_CHUNK * FG_SLOT);
+			const uint32_t ticket = (uint32_t)chunk;
+			const uint32_t len1 = posA - blobBase, len2 = nMates == 2 ? posB - blobBase - (uint32_t)(FG_CHUNK * FG_SLOT) : 0u;
 			if (lane == 0) {
-				P.tileState[ticket] = ((unsigned long long)(pos1 - blobBase) << 31) | (pos2 - blobBase);   // blob lengths, scanned by pass 2
+				P.tileState[ticket] = ((unsigned long long)len1 << 31) | len2;   // blob lengths, scanned by pass 2
 				const uint32_t nPairs = (uint32_t)count;
 				atomicAdd(&P.result->bases, (unsigned long long)(acc & 0xffffu)); atomicAdd(&P.result->hapBytes, (unsigned long long)(acc >> 16));
 				atomicAdd(&P.result->pairs, (unsigned long long)nPairs); atomicAdd(&P.result->reads, (unsigned long long)(nPairs * nMates));
-				atomicAdd(&P.result->rawBytes, (unsigned long long)(pos1 - blobBase) + (pos2 - blobBase));
+				atomicAdd(&P.result->rawBytes, (unsigned long long)len1 + len2);
 			}
 		}
 	}
