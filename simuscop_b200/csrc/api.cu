@@ -169,9 +169,9 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 		if (h->d_slots[0]) cudaFree(h->d_slots[0]);
 		h->d_slots[0] = h->d_slots[1] = nullptr;
 		h->slabPairs = pairs; h->slabCap = cap;
-		// one scratch: the two blobs of a ticket lie side by side (the kernel addresses both from one base pointer)
-		CK(cudaMalloc((void**)&h->d_slots[0], (size_t)pairs * FG_SLOT * nFiles + (size_t)FG_CHUNK * FG_SLOT + 64));
-		h->d_slots[1] = nFiles == 2 ? h->d_slots[0] + (size_t)FG_CHUNK * FG_SLOT : nullptr;
+		// one scratch, file 2's blobs behind file 1's: the kernel addresses both from one base pointer with 32-bit cursors
+		CK(cudaMalloc((void**)&h->d_slots[0], ((size_t)pairs * FG_SLOT + 256) * nFiles));
+		h->d_slots[1] = nFiles == 2 ? h->d_slots[0] + ((size_t)pairs * FG_SLOT + 256) : nullptr;
 		for (int f = 0; f < 2; f++) { if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]); h->d_gzBlobs[f] = nullptr; }
 		CK(h->d_ticket2.alloc(1));
 		CK(h->d_blobPrefix.alloc((size_t)(pairs / 16) + 2));
@@ -269,7 +269,8 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
-		P.blobPitch = (uint32_t)(FG_CHUNK * FG_SLOT) * (h->dt.paired ? 2u : 1u);
+		P.blobPitch = (uint32_t)(FG_CHUNK * FG_SLOT);
+		P.file2Off = (uint32_t)(h->d_slots[1] ? h->d_slots[1] - h->d_slots[0] : 0);
 		cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 		if (h->timeKernels) {
 			while ((int)h->kev.size() < h->kevUsed + 3) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }

@@ -79,8 +79,9 @@ struct GenParams {
 	unsigned long long* blobPrefix;   // fast kernel: exclusive prefix of the blob lengths (pass 2)
 	unsigned int* ticket;
 	unsigned int* ticket2;      // fast kernel: work counter of pass 1 (tickets of FG_CHUNK pairs)
-	uint8_t* out1; uint8_t* out2;       // generic kernel: final slabs; fast kernel: blob scratch (out2 = out1 + one blob when paired)
+	uint8_t* out1; uint8_t* out2;       // generic kernel: final slabs; fast kernel: blob scratch (pass 1: out2 == out1 + file2Off)
 	uint32_t blobPitch;                 // fast kernel: bytes from the blob of ticket j to the blob of ticket j + 1 (pass 1 output, pass 2 / deflate input)
+	uint32_t file2Off;                  // fast kernel, pass 1: file 2's blobs start this many bytes behind file 1's (one allocation, 32-bit cursors)
 	uint8_t* dense1; uint8_t* dense2;   // fast kernel: final slabs (pass 2)
 	unsigned long long cap1, cap2;
 	BatchResult* result;

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_blobs_kernel(const GenParams 
 
 // pass 2b: one warp per blob
 static constexpr int CP_THREADS = 256;
-__global__ void __launch_bounds__(CP_THREADS) move_blobs_kernel(const GenParams P) {
+__global__ void __launch_bounds__(CP_THREADS, 8) move_blobs_kernel(const GenParams P) {
 	const int lane = threadIdx.x & 31;
 	const int nWarps = gridDim.x * (CP_THREADS / 32);
 	for (int j = blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5); j < P.nTiles; j += nWarps) {
@@ -774,10 +774,11 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		const uint32_t nSlots = (uint32_t)(P.emitHi - P.emitLo);
 		const int count = (int)(slot0 + FG_CHUNK < nSlots ? FG_CHUNK : nSlots - slot0);
 		uint32_t acc = 0;                                // bases | haplotype bytes << 16 of this ticket
-		// next free byte of this ticket's two blobs, relative to P.out1 (file 2's blob follows file 1's; scratch < 2^32 bytes).
+		// next free byte of this ticket's two blobs, relative to P.out1 (file 2's blobs lie P.file2Off bytes behind file 1's in the
+		// same allocation; scratch < 2^32 bytes).
 		// posA belongs to the file of the current mate: the two cursors change places after every mate of a pair.
 		const uint32_t blobBase = (uint32_t)chunk * P.blobPitch;
-		uint32_t posA = blobBase, posB = blobBase + (uint32_t)(FG_CHUNK * FG_SLOT);
+		uint32_t posA = blobBase, posB = blobBase + P.file2Off;
 
 		// ---- ticket prologue, lane-parallel: lane L prepares pair slot0 + L (bin, pair ID, fragment draw, header digit counts);
 		// the pair loop below fetches these by shuffle instead of every lane repeating the same scalar work for every pair
@@ -996,7 +997,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		}
 		{
 			const uint32_t ticket = (uint32_t)chunk;
-			const uint32_t len1 = posA - blobBase, len2 = nMates == 2 ? posB - blobBase - (uint32_t)(FG_CHUNK * FG_SLOT) : 0u;
+			const uint32_t len1 = posA - blobBase, len2 = nMates == 2 ? posB - blobBase - P.file2Off : 0u;
 			if (lane == 0) {
 				P.tileState[ticket] = ((unsigned long long)len1 << 31) | len2;   // blob lengths, scanned by pass 2
 				const uint32_t nPairs = (uint32_t)count;
