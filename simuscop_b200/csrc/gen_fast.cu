@@ -2,7 +2,7 @@
 //
 // Same algorithm and bytes as generate_kernel (kernels.cu), engineered for instruction issue,
 // which -- not HBM -- bounds this path (4 uniform draws per base = one Philox4x32-10 block per
-// lane per cycle; the ALU pipe is the busiest unit):
+// lane per cycle; the ALU and FMA-heavy pipes are the busiest units):
 //   * one warp per pair, lane = sequencing cycle, both mates; FG_WORKERS independent warps per
 //     CTA, one CTA per SM; a warp takes FG_CHUNK consecutive pairs per ticket (atomic counter), so
 //     the bin record of a pair is almost always the one of the previous pair and no warp waits
@@ -18,7 +18,11 @@
 //   * cycle -> position-bin offsets are per-lane constants; record terminators ride on the idle
 //     lanes of the last chunk;
 //   * indel candidates and non-ACGT bases are only detected per lane (two compares per chunk, one
-//     vote per read); such reads (about 15 %) take a compact non-unrolled slow path;
+//     vote per read); such reads (about 17 % with the shipped rates) take a compact non-unrolled
+//     path: the events become a sorted list of output segments, the post-indel read is spliced 16
+//     bases per lane out of the packed window into a second packed array, and the per-base work is
+//     the fast path's again (scan_events / splice_read / emit_packed); only reads next to a
+//     non-ACGT base, or grown past the unrolled chunks, go position by position (emit_mapped);
 //   * warps never wait for each other: the records of a ticket are written back to back into that
 //     ticket's blob in an HBM scratch slab (pass 1).  Two small bandwidth-bound kernels then scan
 //     the blob lengths and move every blob (about 10 KB per file) to its exact byte offset with
