@@ -413,7 +413,8 @@ __device__ __forceinline__ void emit_packed(const WarpCtx& w, const uint32_t* wi
 	const int lane = w.lane;
 	const uint32_t inv = (m > 1) ? (0xffffffffu / (uint32_t)m + 1u) : 0xffffffffu;
 	const int chunksM = (m + 31) >> 5;
-	uint8_t* const stB = stage + H + lane;
+	uint8_t* pB = stage + H + lane;                 // this lane's base of the current chunk; its quality follows m + 3 bytes later
+	uint8_t* pQ = pB + m + 3;
 	uint32_t a2[NCH], a3[NCH];
 #pragma unroll
 	for (int k = 0; k < NCH; k++) { a2[k] = x2[k]; a3[k] = x3[k]; }
@@ -446,9 +447,10 @@ __device__ __forceinline__ void emit_packed(const WarpCtx& w, const uint32_t* wi
 			ch = __byte_perm(w.baseChars, 0, 0x4440u | (r16 & 3u));
 		}
 		if (j < m) {
-			stB[c * 32] = (uint8_t)ch;
-			stB[m + 3 + c * 32] = (uint8_t)q;
+			*pB = (uint8_t)ch;
+			*pQ = (uint8_t)q;
 		}
+		pB += 32; pQ += 32;
 	}
 }
 
