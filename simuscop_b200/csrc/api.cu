@@ -473,6 +473,11 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	d.insertRate = t->insert_rate;
 	volatile double one_minus = 1 - t->insert_rate;
 	d.delThresh = t->del_rate / one_minus;
+	{
+		// the conflict-scored bin pitch of the shared quality image must not cost the all-rows-in-shared-memory mode
+		int qm = 0; size_t sb = 0;
+		if (d.qualPitch == 8 && !(ssc::fast_supported(d, h->smemLimit, &qm, &sb) && qm == 8)) d.qualBins = d.B;
+	}
 	h->haveProfile = true;
 	h->havePlan = false;
 	h->haveGz = false;
