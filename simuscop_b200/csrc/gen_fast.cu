@@ -55,7 +55,7 @@ static constexpr int F_LUT_N = 6 * 64;          // context LUT (16-bit entries: 
 
 struct FastLayout {
 	int sub, qual, qualSym, isizeT, isizeSym, insT, insSym, delT, delSym, lut, dig, warp, total;
-	int w_ev, w_insb, w_insp, w_out, w_win, w_hdr, perWarp;
+	int w_ev, w_insb, w_insp, w_out, w_win, perWarp;
 };
 
 __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
@@ -78,7 +78,6 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 	L.w_insp = w; w += 48;                          // inserted bases, packed: one pad word in front, 8 + 1 words
 	L.w_out = w; w += 80;                           // spliced (post-indel) read, packed like a window: one pad word in front, 16 + 1 words
 	L.w_win = w; w += 2 * F_WIN_WORDS * 4;          // one window per mate, filled by cp.async
-	L.w_hdr = w; w += 96;                           // record header of the current pair
 	L.perWarp = w;
 	L.warp = o; o += FG_GEN * L.perWarp;
 	L.total = o;
@@ -735,7 +734,6 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	w.insT = s_insT; w.insSym = s_insSym; w.delT = s_delT; w.delSym = s_delSym;
 	w.win = (const uint32_t*)(wbase + L.w_win);
 	const uint32_t* s_win0 = (const uint32_t*)(wbase + L.w_win);
-	uint8_t* s_hdr = wbase + L.w_hdr;
 	// destination of this lane's window word (cp.async), shared-window address
 	const uint32_t winS = (uint32_t)__cvta_generic_to_shared(wbase + L.w_win) + 4u * lane;
 	w.ev = (uint32_t*)(wbase + L.w_ev); w.insb = wbase + L.w_insb;
@@ -885,7 +883,14 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 					}
 				}
 				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane);
-				s_hdr[i] = (uint8_t)(ch ? ch : dv);                                  // read back by the same lane
+				// straight into both records of the pair (the cursors of file 1 / file 2 are posA / posB here); only the mate
+				// digit in front of the final '\n' differs
+				if (i < H) {
+					const uint32_t hc = ch ? ch : dv;
+					const bool mateDigit = t.paired && i == H - 2;
+					P.out1[posA + i] = (uint8_t)(mateDigit ? '1' : hc);
+					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? '2' : hc);
+				}
 			}
 
 #pragma unroll 1
@@ -915,13 +920,6 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				// any non-ACGT base in the 288-base window also goes the slow way
 				const bool slow = __any_sync(0xffffffffu, cand || (lane >= 16 && lane < 25 && s_win[lane] != 0u)) || P.alwaysSlow;
 
-				// ---- header
-#pragma unroll
-				for (int r = 0; r < 3; r++) {
-					if (r >= hWords) break;
-					const int i = lane + 32 * r;
-					if (i < H) stage[i] = (uint8_t)((t.paired && i == H - 2) ? ('1' + mate) : s_hdr[i]);
-				}
 				int m = RL;
 				if (!slow) {
 					// ---- phase C, fast path (branch free): context straight from the packed window.
