@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 	// window prefetch: lanes 0..15 fetch data words (16 bases each), lanes 16..24 mask words (32 bases each)
 	const uint32_t* winPtr = lane < 16 ? P.hap2 + lane : P.hapN + (lane - 16);
-	const int winShift = lane < 16 ? 4 : 5;
+	const int winHalf = lane < 16 ? 0 : 1;            // a mask word covers 32 bases, a data word 16
 
 	while (true) {
 		// ---- a ticket = FG_CHUNK consecutive pairs
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 		// ---- ticket prologue, lane-parallel: lane L prepares pair slot0 + L (bin, pair ID, fragment draw, header digit counts);
 		// the pair loop below fetches these by shuffle instead of every lane repeating the same scalar work for every pair
-		uint32_t k_pairLo, k_pairHi, k_fstartLo, k_fstartHi, k_flen, k_posmod, k_frag, k_name;
+		uint32_t k_pairLo, k_pairHi, k_winA, k_winB, k_g, k_posmod, k_frag, k_name;
 		{
 			const uint32_t mySlot = slot0 + (uint32_t)(lane < count ? lane : count - 1);
 			const int b0 = P.tileStartBin[chunk];
@@ -825,8 +825,12 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			for (int d = 16; d > 0; d >>= 1) hapB += __shfl_xor_sync(0xffffffffu, hapB, d);
 			acc = hapB << 16;
 			k_pairLo = (uint32_t)pair; k_pairHi = (uint32_t)(pair >> 32);
-			k_fstartLo = (uint32_t)fstart; k_fstartHi = (uint32_t)((uint64_t)fstart >> 32);
-			k_flen = (uint32_t)flen | (seReverse ? 0x80000000u : 0u);
+			// window origins of the two mates (first template base in the store): data word index of base g0 - 32, and the low
+			// five bits of g0 (the mask word index is half the data word index)
+			const int64_t g0b = fstart + flen - RL;
+			const int64_t g0a = seReverse ? g0b : fstart;
+			k_winA = (uint32_t)((uint64_t)(g0a - 32) >> 4); k_winB = (uint32_t)((uint64_t)(g0b - 32) >> 4);
+			k_g = ((uint32_t)g0a & 31u) | (((uint32_t)g0b & 31u) << 8) | (seReverse ? 0x80000000u : 0u);
 			k_posmod = posmod; k_frag = fragCount;
 			// name_off (17 bits) | name_len << 17 (7 bits) | digits of posmod << 24 | digits of fragCount << 28
 			k_name = (uint32_t)bin.name_off | ((uint32_t)bin.name_len << 17) | ((uint32_t)f_ndigits(posmod) << 24) | ((uint32_t)f_ndigits(fragCount) << 28);
@@ -835,22 +839,19 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 #pragma unroll 1
 		for (int p = 0; p < count; p++) {
 			w.c0 = __shfl_sync(0xffffffffu, k_pairLo, p); w.c1 = __shfl_sync(0xffffffffu, k_pairHi, p);
-			const uint32_t flenRev = __shfl_sync(0xffffffffu, k_flen, p);
+			const uint32_t kg = __shfl_sync(0xffffffffu, k_g, p);
 			const uint32_t posmod = __shfl_sync(0xffffffffu, k_posmod, p), fragCount = __shfl_sync(0xffffffffu, k_frag, p);
 			const uint32_t nameNd = __shfl_sync(0xffffffffu, k_name, p);
-			const bool seReverse = (flenRev >> 31) != 0;
+			const bool seReverse = (kg >> 31) != 0;
 
 			// ---- prefetch the packed windows of both mates (data words lanes 0..15, mask words lanes 16..24)
 			// (global -> shared without passing through registers; waited for after phase A of the first mate)
-			uint32_t g0lo;                                   // low five bits of the two window origins
+			const uint32_t g0lo = kg & 0x1f1fu;              // low five bits of the two window origins
 			{
-				const int64_t fstart = (int64_t)(((uint64_t)__shfl_sync(0xffffffffu, k_fstartHi, p) << 32) | __shfl_sync(0xffffffffu, k_fstartLo, p));
-				const int64_t g0b = fstart + (int)(flenRev & 0x7fffffffu) - RL;
-				const int64_t g0a = seReverse ? g0b : fstart;
-				g0lo = ((uint32_t)g0a & 31u) | (((uint32_t)g0b & 31u) << 8);
+				const uint32_t wA = __shfl_sync(0xffffffffu, k_winA, p), wB = __shfl_sync(0xffffffffu, k_winB, p);
 				if (lane < 25) {
-					cp_async4(winS, winPtr + (uint32_t)((uint64_t)(g0a - 32) >> winShift));
-					cp_async4(winS + F_WIN_WORDS * 4, winPtr + (uint32_t)((uint64_t)(g0b - 32) >> winShift));
+					cp_async4(winS, winPtr + (wA >> winHalf));
+					cp_async4(winS + F_WIN_WORDS * 4, winPtr + (wB >> winHalf));
 				}
 				cp_async_commit();
 			}
