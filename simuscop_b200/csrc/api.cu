@@ -266,7 +266,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	if (fast) {
 		grid = std::min((nTiles + FG_GEN - 1) / FG_GEN, h->smCount);
 		if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
-		// pass 1 writes fixed-pitch slots, pass 2 (tickets + look-back over 256-pair tiles) the dense slab
+		// pass 1 writes one blob per ticket and file into the scratch, pass 2 (scan of the blob lengths + one move per blob) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
 		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
 		P.blobPitch = (uint32_t)(FG_CHUNK * FG_SLOT);
