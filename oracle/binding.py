@@ -1,14 +1,15 @@
 """ctypes binding of the CPU oracle (oracle/libssc_oracle.so).
 
 TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline leg.  Nothing on the product path imports this module.
+cpu_baseline leg.  It lives outside the product package (simuscop_b200/) on purpose: nothing
+on the product path imports, links or executes anything under oracle/.
 """
 import ctypes as C
 
 import numpy as np
 
-from . import abi
-from .paths import ORACLE_LIB
+from simuscop_b200 import abi
+from simuscop_b200.paths import ORACLE_LIB
 
 
 class OraclePlan(C.Structure):

@@ -140,7 +140,8 @@ def test_synthetic_profiles_cli_and_abi(name, built, workdir):
     import glob
     import os
     import subprocess
-    from simuscop_b200 import cuda_binding, oracle_binding, paths, synth
+    from oracle import binding as oracle_binding
+    from simuscop_b200 import cuda_binding, paths, synth
     scn = helpers.build_stress(name, workdir)
     plans, out_ref = helpers.run_reference_philox(scn, tag="st")
     plan = planfile.read_plan(plans[0])

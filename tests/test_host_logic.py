@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 
 import helpers
-from simuscop_b200 import cuda_binding, oracle_binding, paths, planfile, sharding, synth
+from oracle import binding as oracle_binding
+from simuscop_b200 import cuda_binding, paths, planfile, sharding, synth
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -136,7 +137,8 @@ _WORKER = r"""
 import os, sys, gzip
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import torch, torch.distributed as dist
-from simuscop_b200 import oracle_binding, planfile, sharding
+from oracle import binding as oracle_binding
+from simuscop_b200 import planfile, sharding
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 plan = planfile.read_plan(sys.argv[2])

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import helpers
-from simuscop_b200 import oracle_binding, planfile
+from oracle import binding as oracle_binding
+from simuscop_b200 import planfile
 from simuscop_b200.paths import REF_PHILOX
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
