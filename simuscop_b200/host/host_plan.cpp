@@ -99,6 +99,11 @@ void Job::phase_segment(Segment& seg) {
 			}
 			if (i >= 0) {
 				n -= i;
+				// the remaining copies go to the other haplotype indices; a haploid genome has none and the reference spins
+				// forever in this loop (Segment.cpp:183-189) -- reject instead of hanging
+				if (n > 0 && ploidy < 2)
+					die(1, "ERROR: copy number " + std::to_string(CN) + " with major copy number " + std::to_string(mCN) + " cannot be phased with ploidy " +
+					           std::to_string(ploidy) + " (" + seg.chr + ":" + std::to_string(seg.start) + ")");
 				while (n > 0) { int j = (int)rand_int(0, ploidy); if (j != k) { seg.seqReps[j]++; n--; } }
 			} else {
 				while (n > 0) { int j = (int)rand_int(0, ploidy); seg.seqReps[j]++; n--; }

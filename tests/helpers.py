@@ -143,6 +143,57 @@ def build_scenario(name, workdir, seed=7):
     return dict(dir=d, kw=kw, seed=seed, name=name)
 
 
+def build_random_variation_scenario(seed, workdir):
+    """A seeded random job for the plan-construction fuzz test: one chromosome, disjoint CNVs (copy numbers 1..5 with a random
+    major copy number), insertions / deletions / SNVs (homo- and heterozygous) in shuffled file order, ploidy 1..3, PE or SE."""
+    import random
+    rng = random.Random(seed)
+    L = rng.choice([400000, 900000, 1500000])
+    d = os.path.join(workdir, "fuzz%d" % seed)
+    os.makedirs(d, exist_ok=True)
+    data = testdata.materialize(os.path.join(workdir, "data"))
+    synth.make_genome(os.path.join(d, "ref.fa"), [L], seed=seed, names=["chr20"], n_runs=rng.randint(0, 2),
+                      lower_runs=rng.randint(0, 2), run_len=300)
+    with open(os.path.join(d, "ref.fa")) as f:
+        ref = f.read().split("\n", 1)[1].replace("\n", "").upper()
+    ploidy = rng.choice([1, 2, 2, 3])
+    lines = []
+    pos = 50001
+    while pos + 150000 < L and rng.random() < 0.8:
+        ln = rng.choice([60000, 100000, 250000])
+        if pos + ln > L:
+            break
+        cn = rng.choice([1, 3, 4, 5])
+        # a haploid genome cannot split a gain between two haplotype sets: the reference spins forever in
+        # Segment.cpp:183-189 unless every copy is "major" (our front end rejects that input, test_host_logic)
+        major = cn if ploidy == 1 else rng.randint((cn + 1) // 2, cn)
+        lines.append("c\ttest\tchr20\t%d\t%d\t%d\t%d" % (pos, pos + ln - 1, cn, major))
+        pos += ln + rng.choice([1, 40000, 120000])
+    used = set()
+    for _ in range(rng.randint(3, 12)):
+        p = rng.randint(2000, L - 2000)
+        if any(abs(p - u) < 200 for u in used):
+            continue
+        used.add(p)
+        z = rng.choice(["homo", "het"])
+        k = rng.random()
+        if k < 0.35:
+            lines.append("i\ttest\tchr20\t%d\t%s\t%s" % (p, "".join(rng.choice("acgt") for _ in range(rng.randint(1, 12))), z))
+        elif k < 0.7:
+            lines.append("d\ttest\tchr20\t%d\t%d\t%s" % (p, rng.randint(1, 15), z))
+        elif ref[p - 1] in "ACGT":
+            lines.append("s\ttest\tchr20\t%d\t%s\t%s\t%s" % (p, ref[p - 1], rng.choice([b for b in "ACGT" if b != ref[p - 1]]), z))
+    rng.shuffle(lines)
+    with open(os.path.join(d, "variations.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    kw = dict(ref=os.path.join(d, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[rng.choice(["XTen", "GAIIx", "HiSeq2500"])]),
+              layout=rng.choice(["PE", "SE"]), coverage=1, insertSize=rng.choice([200, 300]), threads=1, verbose=0, name="test",
+              variation=os.path.join(d, "variations.txt"))
+    if ploidy != 2:
+        kw["ploidy"] = ploidy
+    return dict(dir=d, kw=kw, seed=seed, name="fuzz%d" % seed)
+
+
 def run_reference_philox(scn, tag="ref"):
     """Runs the instrumented reference; returns (list of plan paths, sorted list of fastq paths)."""
     d = scn["dir"]

@@ -13,7 +13,7 @@ import pytest
 
 import helpers
 from oracle import binding as oracle_binding
-from simuscop_b200 import cuda_binding, paths, planfile, sharding, synth
+from simuscop_b200 import cuda_binding, paths, planfile, sharding, synth, testdata
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -108,6 +108,37 @@ def test_host_plan_matches_golden_hashes(name, built, workdir):
     assert len(ours) == len(gold["samples"])
     for pf, s in zip(ours, gold["samples"]):
         assert hashlib.sha256(open(pf, "rb").read()).hexdigest() == s["plan_sha256"]
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_host_plan_equals_the_instrumented_reference_on_random_variation_sets(seed, built, workdir):
+    """Plan-construction fuzz (CPU only): random CNV / insertion / deletion / SNV files, ploidy 1..3, PE and SE.  The plan dump of the
+    C++ front end (tables, rand()-phased haplotypes, bins, read counts) must equal the instrumented reference's dump byte for byte."""
+    if not os.path.exists(paths.REF_PHILOX):
+        pytest.skip("oracle/_ref/simuReads_philox not built (needs /root/reference)")
+    scn = helpers.build_random_variation_scenario(seed, workdir)
+    ref_plans, _ = helpers.run_reference_philox(scn, tag="ref")
+    ours = _plan_only(scn, "ours")
+    assert len(ours) == len(ref_plans) > 0
+    for a, b in zip(ours, ref_plans):
+        assert open(a, "rb").read() == open(b, "rb").read(), (seed, open(scn["kw"]["variation"]).read())
+
+
+def test_unphaseable_haploid_gain_is_rejected_not_spun_on(built, tmp_path):
+    """ploidy 1 with a copy-number gain whose major copy number is smaller than the copy number: the reference never leaves the
+    loop at Segment.cpp:183-189 (it looks for a second haplotype index); the replacement reports the segment and exits."""
+    d = str(tmp_path)
+    synth.make_genome(os.path.join(d, "ref.fa"), [300000], seed=3, names=["chr20"])
+    with open(os.path.join(d, "variations.txt"), "w") as f:
+        f.write("c\ttest\tchr20\t100001\t200000\t4\t3\n")
+    data = testdata.materialize(os.path.join(d, "data"))
+    cfg = os.path.join(d, "cfg.txt")
+    synth.write_config(cfg, output=os.path.join(d, "out"), ref=os.path.join(d, "ref.fa"), profile=os.path.join(data, testdata.PROFILES["XTen"]),
+                       layout="PE", coverage=1, insertSize=300, threads=1, verbose=0, name="test", ploidy=1,
+                       variation=os.path.join(d, "variations.txt"))
+    r = subprocess.run([paths.SIMUREADS, cfg], env=dict(os.environ, SIMUSCOP_PLAN_ONLY="1", SIMUSCOP_DUMP_PLAN=os.path.join(d, "plan"), SIMUSCOP_SEED="1"), capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 1 and "cannot be phased with ploidy 1" in r.stderr, r.stderr[-500:]
 
 
 def test_cli_argument_and_config_errors(built, tmp_path):
