@@ -194,6 +194,105 @@ def build_random_variation_scenario(seed, workdir):
     return dict(dir=d, kw=kw, seed=seed, name="fuzz%d" % seed)
 
 
+def build_random_job_scenario(seed, workdir):
+    """A seeded random job over the other inputs of the front end: 1..3 chromosomes, capture targets (BED intervals from 30 bp to
+    2.6 kb, touching / close / far apart), SNP files on both strands, tumour mixtures (2..3 populations x 1..2 abundance rows) with
+    per-population variations.  Returns (scenario, mode)."""
+    import random
+    rng = random.Random(seed)
+    nchr = rng.choice([1, 2, 3])
+    lens = [rng.choice([120000, 400000, 700000]) for _ in range(nchr)]
+    names = ["chr%d" % (20 + i) for i in range(nchr)]
+    d = os.path.join(workdir, "job%d" % seed)
+    os.makedirs(d, exist_ok=True)
+    data = testdata.materialize(os.path.join(workdir, "data"))
+    synth.make_genome(os.path.join(d, "ref.fa"), lens, seed=seed, names=names, n_runs=rng.randint(0, 2), lower_runs=rng.randint(0, 1),
+                      run_len=300)
+    with open(os.path.join(d, "ref.fa")) as f:
+        recs = f.read().split(">")[1:]
+    refs = {t.split("\n", 1)[0].split()[0]: t.split("\n", 1)[1].replace("\n", "").upper() for t in recs}
+    kw = dict(ref=os.path.join(d, "ref.fa"),
+              profile=os.path.join(data, testdata.PROFILES[rng.choice(["XTen", "GAIIx", "HiSeq2500", "HiSeq2000"])]),
+              layout=rng.choice(["PE", "SE"]), coverage=rng.choice([1, 2]), insertSize=rng.choice([200, 300]), threads=1, verbose=0,
+              name="test")
+    mode = rng.choice(["wes", "snp", "tumor", "wes+var"])
+    pops = ["test"]
+    if mode == "tumor":
+        pops = ["c1", "c2", "c3"][:rng.choice([2, 3])]
+        kw["name"] = ",".join(pops)
+        rows = []
+        for _ in range(rng.choice([1, 2])):
+            w = [rng.randint(1, 9) for _ in pops]
+            w = [x * 100 // sum(w) for x in w]
+            w[0] += 100 - sum(w)                                   # rows sum to exactly 1 (the front end checks)
+            rows.append("\t".join("%.2f" % (x / 100.0) for x in w))
+        with open(os.path.join(d, "abundance.txt"), "w") as f:
+            f.write("\n".join(rows) + "\n")
+        kw["abundance"] = os.path.join(d, "abundance.txt")
+    if mode in ("tumor", "wes+var", "snp"):
+        lines = []
+        for pop in pops:
+            for c, L in zip(names, lens):
+                pos = 20001
+                while pos + 80000 < L and rng.random() < 0.6:
+                    ln = rng.choice([30000, 60000])
+                    cn = rng.choice([1, 3, 4])
+                    lines.append("c\t%s\t%s\t%d\t%d\t%d\t%d" % (pop, c, pos, pos + ln - 1, cn, rng.randint((cn + 1) // 2, cn)))
+                    pos += ln + rng.choice([1, 30000])
+                used = set()
+                for _ in range(rng.randint(0, 6)):
+                    p = rng.randint(2000, L - 2000)
+                    if any(abs(p - u) < 200 for u in used):
+                        continue
+                    used.add(p)
+                    z = rng.choice(["homo", "het"])
+                    k = rng.random()
+                    if k < 0.35:
+                        lines.append("i\t%s\t%s\t%d\t%s\t%s" % (pop, c, p, "".join(rng.choice("acgt") for _ in range(rng.randint(1, 9))), z))
+                    elif k < 0.7:
+                        lines.append("d\t%s\t%s\t%d\t%d\t%s" % (pop, c, p, rng.randint(1, 12), z))
+                    elif refs[c][p - 1] in "ACGT":
+                        lines.append("s\t%s\t%s\t%d\t%s\t%s\t%s" % (pop, c, p, refs[c][p - 1],
+                                                                   rng.choice([b for b in "ACGT" if b != refs[c][p - 1]]), z))
+        rng.shuffle(lines)
+        if lines:
+            with open(os.path.join(d, "variations.txt"), "w") as f:
+                f.write("\n".join(lines) + "\n")
+            kw["variation"] = os.path.join(d, "variations.txt")
+    if mode == "snp" or rng.random() < 0.3:
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        sl = []
+        for c, L in zip(names, lens):
+            for i in range(rng.randint(1, 30)):
+                p = rng.randint(100, L - 100)
+                r = refs[c][p - 1]
+                if r not in "ACGT":
+                    continue
+                alt = rng.choice([b for b in "ACGT" if b != r])
+                strand = rng.choice("+-")
+                a, b = (r, alt) if strand == "+" else (comp[r], comp[alt])
+                sl.append((c, p, "rs%d\t%s\t%d\t%s\t%s\t%s" % (seed * 1000 + i, c, p, "%s/%s" % ((a, b) if rng.random() < 0.5 else (b, a)),
+                                                               strand, a)))
+        sl.sort()
+        with open(os.path.join(d, "snp.txt"), "w") as f:
+            f.write("\n".join(x[2] for x in sl) + "\n")
+        kw["snp"] = os.path.join(d, "snp.txt")
+    if mode in ("wes", "wes+var"):
+        bl = []
+        for c, L in zip(names, lens):
+            p = rng.randint(100, 3000)
+            while p < L - 200:
+                e = min(p + rng.choice([60, 150, 400, 1200, 2600]), L - 60)
+                if e - p > 30:
+                    bl.append("%s\t%d\t%d" % (c, p, e))
+                p = e + rng.choice([1, 30, 90, 2000, 20000])
+        with open(os.path.join(d, "targets.bed"), "w") as f:
+            f.write("\n".join(bl) + "\n")
+        kw["target"] = os.path.join(d, "targets.bed")
+        kw["coverage"] = 10
+    return dict(dir=d, kw=kw, seed=seed, name="job%d" % seed), mode
+
+
 def run_reference_philox(scn, tag="ref"):
     """Runs the instrumented reference; returns (list of plan paths, sorted list of fastq paths)."""
     d = scn["dir"]

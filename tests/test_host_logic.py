@@ -124,6 +124,20 @@ def test_host_plan_equals_the_instrumented_reference_on_random_variation_sets(se
         assert open(a, "rb").read() == open(b, "rb").read(), (seed, open(scn["kw"]["variation"]).read())
 
 
+@pytest.mark.parametrize("seed", [1, 2, 7, 16, 19, 24, 25, 29])
+def test_host_plan_equals_the_instrumented_reference_on_random_jobs(seed, built, workdir):
+    """The same fuzz over the other inputs: multi-chromosome genomes, capture targets, SNP files on both strands, tumour mixtures
+    with per-population variations (seeds chosen to cover every mode)."""
+    if not os.path.exists(paths.REF_PHILOX):
+        pytest.skip("oracle/_ref/simuReads_philox not built (needs /root/reference)")
+    scn, mode = helpers.build_random_job_scenario(seed, workdir)
+    ref_plans, _ = helpers.run_reference_philox(scn, tag="ref")
+    ours = _plan_only(scn, "ours")
+    assert len(ours) == len(ref_plans) > 0, mode
+    for a, b in zip(ours, ref_plans):
+        assert open(a, "rb").read() == open(b, "rb").read(), (seed, mode)
+
+
 def test_unphaseable_haploid_gain_is_rejected_not_spun_on(built, tmp_path):
     """ploidy 1 with a copy-number gain whose major copy number is smaller than the copy number: the reference never leaves the
     loop at Segment.cpp:183-189 (it looks for a second haplotype index); the replacement reports the segment and exits."""
