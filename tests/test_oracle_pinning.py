@@ -79,6 +79,21 @@ def test_oracle_matches_live_instrumented_reference(name, built, workdir):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
+@pytest.mark.parametrize("seed", [2, 16, 19, 25, 31, 44])
+def test_oracle_matches_live_instrumented_reference_on_random_jobs(seed, built, workdir):
+    """Fuzz pin: seeded random jobs (capture targets, SNPs, tumour mixtures, CNV / indel / SNV variations, 1..3 chromosomes, PE and
+    SE, all four shipped profiles): every FASTQ byte of the oracle equals the instrumented reference's, for every sample."""
+    scn, mode = helpers.build_random_job_scenario(seed, workdir)
+    plans, out = helpers.run_reference_philox(scn, tag="pinfz")
+    assert plans, mode
+    for i, pf in enumerate(plans):
+        plan = planfile.read_plan(pf)
+        r1p, r2p = helpers.sample_files(out, plan, i, scn)
+        f1, f2, info = oracle_binding.generate(plan, scn["seed"])
+        assert f1 == helpers.read_file(r1p) and f2 == helpers.read_file(r2p), (seed, mode, i)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
 @pytest.mark.parametrize("name", sorted(helpers.STRESS))
 def test_oracle_and_host_on_synthetic_profiles(name, built, workdir):
     """Synthetic profiles with odd k-mer sizes, short/long reads, heavy indels, degenerate rows: the oracle and the
