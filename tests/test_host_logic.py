@@ -169,6 +169,71 @@ def test_cli_argument_and_config_errors(built, tmp_path):
     assert r.returncode == 1 and "sequencing profile must be specified" in r.stderr
 
 
+def test_config_matrix_behaves_like_the_reference(built, tmp_path):
+    """Config grammar and validation (lib/config/Config.cpp:46-99 and the checks of simuReads.cpp): for a matrix of missing keys,
+    bad values, missing input files and formatting variants, the replacement CLI exits with the reference's code and last
+    message, and on success dumps the reference's plan byte for byte.  Where the reference dies of an uncaught exception
+    (insertSize below the read length: std::bad_array_new_length, SIGABRT) the replacement reports the problem and exits 1."""
+    if not os.path.exists(paths.REF_PHILOX):
+        pytest.skip("oracle/_ref/simuReads_philox not built (needs /root/reference)")
+    wd = str(tmp_path)
+    data = testdata.materialize(os.path.join(wd, "data"))
+    synth.make_genome(os.path.join(wd, "ref.fa"), [60000], seed=3, names=["chr20"])
+    base = dict(ref=os.path.join(wd, "ref.fa"), profile=os.path.join(data, testdata.PROFILES["GAIIx"]), name="test",
+                output=os.path.join(wd, "out"), layout="PE", threads="1", verbose="0", coverage="1", insertSize="250")
+    nope = os.path.join(wd, "nope")
+    cases = [("ok", {})] + [("missing_" + k, {k: None}) for k in base]
+    cases += [("coverage=" + v, dict(coverage=v)) for v in ("-1", "0", "abc", "0.5")]
+    cases += [("layout=" + v, dict(layout=v)) for v in ("XX", "pe", "SE")]
+    cases += [("threads=" + v, dict(threads=v)) for v in ("0", "-2", "999")]
+    cases += [("ploidy=" + v, dict(ploidy=v)) for v in ("0", "-1", "5")]
+    cases += [("insertSize=-5", dict(insertSize="-5")), ("name=a,b", dict(name="a,b")), ("verbose=2", dict(verbose="2"))]
+    cases += [(k + "=missing file", {k: nope}) for k in ("ref", "profile", "variation", "snp", "target", "abundance")]
+    body = ["%s = %s" % kv for kv in base.items()]
+    raws = [("comments", "# c\n" + "\n".join(body) + "\n"), ("no spaces", "\n".join(l.replace(" = ", "=") for l in body) + "\n"),
+            ("tabs", "\n".join(l.replace(" = ", "\t=\t") for l in body) + "\n"), ("duplicate key", "\n".join(body) + "\ncoverage = 2\n"),
+            ("blank lines", "\n\n".join(body) + "\n\n"), ("no equals sign", "\n".join(body) + "\njunk line\n"),
+            ("empty value", "\n".join(body) + "\nsnp = \n"), ("trailing blanks", "\n".join(l + "  " for l in body) + "\n"),
+            ("crlf", "\r\n".join(body) + "\r\n")]
+
+    def run(binary, tag, text):
+        cfg = os.path.join(wd, "c_%s.txt" % tag)
+        with open(cfg, "w") as f:
+            f.write(text)
+        for f in glob.glob(os.path.join(wd, "p_%s.*" % tag)):
+            os.remove(f)
+        env = dict(os.environ, SIMUSCOP_SEED="1", SIMUSCOP_DUMP_PLAN=os.path.join(wd, "p_" + tag))
+        if tag == "ours":
+            env["SIMUSCOP_PLAN_ONLY"] = "1"
+        r = subprocess.run([binary, cfg], env=env, capture_output=True, text=True, timeout=120, cwd=wd)
+        msg = [l for l in (r.stderr + r.stdout).strip().split("\n") if l.strip()]
+        return r.returncode, (msg[-1] if msg else ""), sorted(glob.glob(os.path.join(wd, "p_%s.*.plan" % tag)))
+
+    def text_of(chg):
+        kw = dict(base)
+        for k, v in chg.items():
+            if v is None:
+                kw.pop(k, None)
+            else:
+                kw[k] = v
+        return "".join("%s = %s\n" % kv for kv in kw.items())
+
+    for label, text in [(l, text_of(c)) for l, c in cases] + raws:
+        rc_r, msg_r, plans_r = run(paths.REF_PHILOX, "ref", text)
+        rc_o, msg_o, plans_o = run(paths.SIMUREADS, "ours", text)
+        assert rc_r == rc_o, (label, rc_r, rc_o, msg_r, msg_o)
+        if rc_r != 0:
+            assert msg_r == msg_o, (label, msg_r, msg_o)
+        else:
+            assert len(plans_r) == len(plans_o) > 0, label
+            for a, b in zip(plans_r, plans_o):
+                assert open(a, "rb").read() == open(b, "rb").read(), label
+    # the reference aborts here; the replacement says why
+    rc_r, _, _ = run(paths.REF_PHILOX, "ref", text_of(dict(insertSize="50")))
+    rc_o, msg_o, _ = run(paths.SIMUREADS, "ours", text_of(dict(insertSize="50")))
+    assert rc_r < 0 and rc_o == 1 and "insert size" in msg_o
+
+
 def test_shard_ranges_partition():
     for planned in (0, 1, 7, 1000, 298013245):
         for world in (1, 2, 3, 8):
