@@ -293,6 +293,64 @@ def build_random_job_scenario(seed, workdir):
     return dict(dir=d, kw=kw, seed=seed, name="job%d" % seed), mode
 
 
+def build_edge_variation_scenario(seed, workdir):
+    """Seeded variation files that sit on the edges of the reference's segment logic: overlapping CNVs (the 1-bp overlapping
+    segments of Genome.cpp:663-674), variants at position 1 / the last base / beyond the end, dense indel + SNV clusters,
+    deletions and insertions across CNV boundaries, variants inside N runs, chromosomes the FASTA does not have.  Returns
+    (scenario, kind)."""
+    import random
+    rng = random.Random(seed)
+    wd = os.path.join(workdir, "edge%d" % seed)
+    os.makedirs(wd, exist_ok=True)
+    data = testdata.materialize(os.path.join(workdir, "data"))
+    L = rng.choice([30000, 90000, 250000])
+    synth.make_genome(os.path.join(wd, "ref.fa"), [L, 8000], seed=seed, names=["chr20", "chr21"], n_runs=rng.randint(0, 2), lower_runs=1, run_len=200)
+    ref = open(os.path.join(wd, "ref.fa")).read().split(">")[1].split("\n", 1)[1].replace("\n", "").upper()
+    lines = []
+    kind = rng.choice(["overlap_cnv", "edge_pos", "dense", "beyond_end", "unknown_chr", "n_region", "del_cross_cnv", "mixed"])
+    def snv(p, z=None):
+        if 1 <= p <= L and ref[p-1] in "ACGT": lines.append("s\ttest\tchr20\t%d\t%s\t%s\t%s" % (p, ref[p-1], rng.choice([b for b in "ACGT" if b != ref[p-1]]), z or rng.choice(["homo", "het"])))
+    if kind == "overlap_cnv":
+        a = rng.randint(2000, L // 3); b = a + rng.randint(3000, L // 3)
+        lines.append("c\ttest\tchr20\t%d\t%d\t3\t2" % (a, b)); lines.append("c\ttest\tchr20\t%d\t%d\t1\t1" % (b, min(L, b + rng.randint(3000, 9000))))
+    elif kind == "edge_pos":
+        lines.append("i\ttest\tchr20\t1\tacgt\thomo"); lines.append("d\ttest\tchr20\t%d\t3\thet" % (L - 5)); snv(1); snv(L)
+        lines.append("i\ttest\tchr20\t%d\tgg\thet" % L)
+        lines.append("c\ttest\tchr20\t1\t%d\t3\t2" % rng.randint(2000, L // 2))
+    elif kind == "dense":
+        p = rng.randint(1000, L - 2000)
+        for i in range(rng.randint(3, 8)):
+            k = rng.random(); q = p + i * rng.randint(1, 12)
+            if k < 0.4: lines.append("i\ttest\tchr20\t%d\t%s\t%s" % (q, "".join(rng.choice("acgt") for _ in range(rng.randint(1, 6))), rng.choice(["homo", "het"])))
+            elif k < 0.7: lines.append("d\ttest\tchr20\t%d\t%d\t%s" % (q, rng.randint(1, 9), rng.choice(["homo", "het"])))
+            else: snv(q)
+    elif kind == "beyond_end":
+        lines.append("d\ttest\tchr20\t%d\t50\thomo" % (L - 10)); lines.append("c\ttest\tchr20\t%d\t%d\t3\t2" % (L - 5000, L + 5000)); lines.append("i\ttest\tchr20\t%d\tacg\thomo" % (L + 100))
+    elif kind == "unknown_chr":
+        lines.append("s\ttest\tchr5\t100\tA\tC\thomo"); lines.append("c\ttest\tchrX\t1000\t5000\t3\t2"); snv(rng.randint(100, L - 100))
+    elif kind == "n_region":
+        idx = ref.find("N")
+        if idx >= 0:
+            lines.append("i\ttest\tchr20\t%d\tacgt\thomo" % (idx + 5)); lines.append("d\ttest\tchr20\t%d\t20\thet" % (idx + 50)); lines.append("c\ttest\tchr20\t%d\t%d\t3\t3" % (max(1, idx - 3000), min(L, idx + 3000)))
+    elif kind == "del_cross_cnv":
+        a = rng.randint(3000, L // 2); b = a + 5000
+        lines.append("c\ttest\tchr20\t%d\t%d\t3\t2" % (a, b)); lines.append("d\ttest\tchr20\t%d\t12\thomo" % (a - 5)); lines.append("d\ttest\tchr20\t%d\t12\thet" % (b - 5)); lines.append("i\ttest\tchr20\t%d\taa\thomo" % a); lines.append("i\ttest\tchr20\t%d\tcc\thet" % b)
+    else:
+        for _ in range(rng.randint(5, 25)):
+            p = rng.randint(1, L); k = rng.random()
+            if k < 0.3: lines.append("i\ttest\tchr20\t%d\t%s\t%s" % (p, "".join(rng.choice("acgtn") for _ in range(rng.randint(1, 20))), rng.choice(["homo", "het"])))
+            elif k < 0.6: lines.append("d\ttest\tchr20\t%d\t%d\t%s" % (p, rng.randint(1, 40), rng.choice(["homo", "het"])))
+            elif k < 0.9: snv(p)
+            else:
+                e = min(L, p + rng.randint(1000, 20000)); lines.append("c\ttest\tchr20\t%d\t%d\t%d\t%d" % (p, e, rng.choice([1,3,4]), 2))
+    rng.shuffle(lines)
+    open(os.path.join(wd, "variations.txt"), "w").write("\n".join(lines) + "\n")
+    kw = dict(ref=os.path.join(wd, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[rng.choice(["XTen", "GAIIx"])]), layout=rng.choice(["PE", "SE"]), coverage=1,
+              insertSize=rng.choice([200, 300]), threads=1, verbose=0, name="test", variation=os.path.join(wd, "variations.txt"))
+    if rng.random() < 0.3: kw["ploidy"] = 3
+    return dict(dir=wd, kw=kw, seed=seed, name="edge%d" % seed), kind
+
+
 def run_reference_philox(scn, tag="ref"):
     """Runs the instrumented reference; returns (list of plan paths, sorted list of fastq paths)."""
     d = scn["dir"]

@@ -138,6 +138,37 @@ def test_host_plan_equals_the_instrumented_reference_on_random_jobs(seed, built,
         assert open(a, "rb").read() == open(b, "rb").read(), (seed, mode)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 3, 5, 6, 7, 14, 17, 53])
+def test_host_plan_equals_the_instrumented_reference_on_edge_case_variations(seed, built, workdir):
+    """One seed per kind of helpers.build_edge_variation_scenario (53: an input both programs reject with the same message)."""
+    if not os.path.exists(paths.REF_PHILOX):
+        pytest.skip("oracle/_ref/simuReads_philox not built (needs /root/reference)")
+    scn, kind = helpers.build_edge_variation_scenario(seed, workdir)
+    d = scn["dir"]
+
+    def run(binary, tag):
+        cfg = os.path.join(d, "cfg_%s.txt" % tag)
+        synth.write_config(cfg, output=os.path.join(d, "out_" + tag), **scn["kw"])
+        for f in glob.glob(os.path.join(d, "p_%s.*" % tag)):
+            os.remove(f)
+        env = dict(os.environ, SIMUSCOP_SEED=str(seed), SIMUSCOP_DUMP_PLAN=os.path.join(d, "p_" + tag))
+        if tag == "ours":
+            env["SIMUSCOP_PLAN_ONLY"] = "1"
+        r = subprocess.run([binary, cfg], env=env, capture_output=True, text=True, timeout=120, cwd=d)
+        msg = [l for l in (r.stderr + r.stdout).strip().split("\n") if l.strip()]
+        return r.returncode, (msg[-1] if msg else ""), sorted(glob.glob(os.path.join(d, "p_%s.*.plan" % tag)))
+
+    rc_r, msg_r, plans_r = run(paths.REF_PHILOX, "ref")
+    rc_o, msg_o, plans_o = run(paths.SIMUREADS, "ours")
+    assert rc_r == rc_o, (kind, rc_r, rc_o, msg_r, msg_o)
+    if rc_r != 0:
+        assert msg_r == msg_o, kind
+    else:
+        assert len(plans_r) == len(plans_o) > 0, kind
+        for a, b in zip(plans_r, plans_o):
+            assert open(a, "rb").read() == open(b, "rb").read(), kind
+
+
 def test_unphaseable_haploid_gain_is_rejected_not_spun_on(built, tmp_path):
     """ploidy 1 with a copy-number gain whose major copy number is smaller than the copy number: the reference never leaves the
     loop at Segment.cpp:183-189 (it looks for a second haplotype index); the replacement reports the segment and exits."""
