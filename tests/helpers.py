@@ -351,6 +351,65 @@ def build_edge_variation_scenario(seed, workdir):
     return dict(dir=wd, kw=kw, seed=seed, name="edge%d" % seed), kind
 
 
+EDGE_INPUT_KINDS = ["bed_overlap", "bed_beyond", "bed_tiny", "bed_unknown_chr", "bed_unsorted", "bed_start_gt_end", "snp_mismatch_ref", "snp_dup", "snp_unknown_chr", "snp_beyond", "snp_bad_strand",
+                   "abund_not_one", "abund_cols", "abund_zero", "bed_plus_cnv", "snp_in_cnv_indel"]
+
+
+def build_edge_input_scenario(seed, workdir):
+    """Edge cases of the other input files (kind = EDGE_INPUT_KINDS[seed % 16]): capture targets that overlap, run past the
+    chromosome end, are tiny / unsorted / inverted / on unknown chromosomes; SNP lines whose reference allele does not match,
+    duplicates, unknown chromosomes, positions beyond the end, an unknown strand symbol; abundance rows that do not sum to one,
+    have the wrong number of columns or zero entries; targets and SNPs inside CNVs and indels.  Returns (scenario, kind)."""
+    import random
+    rng = random.Random(seed)
+    kind = EDGE_INPUT_KINDS[seed % len(EDGE_INPUT_KINDS)]
+    wd = os.path.join(workdir, "input%d" % seed)
+    os.makedirs(wd, exist_ok=True)
+    data = testdata.materialize(os.path.join(workdir, "data"))
+    L = rng.choice([40000, 120000])
+    synth.make_genome(os.path.join(wd, "ref.fa"), [L, 9000], seed=seed, names=["chr20", "chr21"], n_runs=rng.randint(0, 1), lower_runs=1, run_len=200)
+    ref = open(os.path.join(wd, "ref.fa")).read().split(">")[1].split("\n", 1)[1].replace("\n", "").upper()
+    kw = dict(ref=os.path.join(wd, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[rng.choice(["XTen", "HiSeq2500"])]), layout=rng.choice(["PE", "SE"]), coverage=5,
+              insertSize=rng.choice([200, 300]), threads=1, verbose=0, name="test")
+    bed, snp, var, ab = [], [], [], None
+    def snpline(c, p, strand="+", r=None, alt=None, first=None, i=0):
+        r = r or (ref[p-1] if c == "chr20" and 1 <= p <= L else "A"); alt = alt or rng.choice([b for b in "ACGT" if b != r])
+        return "rs%d\t%s\t%d\t%s/%s\t%s\t%s" % (seed * 100 + i, c, p, r, alt, strand, first or r)
+    if kind == "bed_overlap":
+        p = 2000
+        for i in range(8): bed.append(("chr20", p, p + rng.randint(200, 1500))); p += rng.randint(50, 600)
+    elif kind == "bed_beyond": bed += [("chr20", L - 300, L + 500), ("chr20", L + 1000, L + 2000), ("chr20", 5000, 5600)]
+    elif kind == "bed_tiny": bed += [("chr20", 3000, 3001), ("chr20", 4000, 4010), ("chr20", 1, 40), ("chr20", 10, 30), ("chr20", 8000, 8900)]
+    elif kind == "bed_unknown_chr": bed += [("chr7", 100, 900), ("chr20", 3000, 3900), ("chr21", 100, 700)]
+    elif kind == "bed_unsorted": bed += [("chr20", 9000, 9800), ("chr20", 2000, 2900), ("chr21", 500, 900), ("chr20", 5000, 5200)]
+    elif kind == "bed_start_gt_end": bed += [("chr20", 5000, 4000), ("chr20", 7000, 7900)]
+    elif kind == "snp_mismatch_ref": snp += [snpline("chr20", p, r=rng.choice("ACGT"), i=i) for i, p in enumerate(sorted(rng.sample(range(100, L - 100), 12)))]
+    elif kind == "snp_dup":
+        p = rng.randint(100, L - 100); snp += [snpline("chr20", p, i=0), snpline("chr20", p, i=1), snpline("chr20", p + 1, i=2)]
+    elif kind == "snp_unknown_chr": snp += [snpline("chr9", 500, i=0), snpline("chr20", 700, i=1)]
+    elif kind == "snp_beyond": snp += [snpline("chr20", L + 50, i=0), snpline("chr20", L, i=1), snpline("chr20", 1, i=2)]
+    elif kind == "snp_bad_strand": snp += [snpline("chr20", 900, strand="?", i=0), snpline("chr20", 1900, strand="-", i=1)]
+    elif kind.startswith("abund"):
+        kw["name"] = "c1,c2"
+        ab = {"abund_not_one": "0.5\t0.4\n", "abund_cols": "0.5\t0.3\t0.2\n", "abund_zero": "1.0\t0.0\n0.0\t1.0\n"}[kind]
+        var += ["c\tc1\tchr20\t5001\t15000\t3\t2", "s\tc2\tchr20\t%d\t%s\t%s\thomo" % (3000, ref[2999] if ref[2999] in "ACGT" else "A", "C" if ref[2999] != "C" else "G")]
+    elif kind == "bed_plus_cnv":
+        bed += [("chr20", 4000, 5200), ("chr20", 9500, 10400), ("chr20", 14800, 15300)]
+        var += ["c\ttest\tchr20\t5001\t10000\t3\t2", "c\ttest\tchr20\t10001\t15000\t1\t1", "d\ttest\tchr20\t4990\t30\thomo", "i\ttest\tchr20\t9999\tacgtacgt\thet"]
+    elif kind == "snp_in_cnv_indel":
+        var += ["c\ttest\tchr20\t5001\t10000\t4\t3", "d\ttest\tchr20\t7000\t10\thet", "i\ttest\tchr20\t7100\tacg\thomo"]
+        snp += [snpline("chr20", p, i=i) for i, p in enumerate([5001, 6999, 7000, 7005, 7010, 7100, 7101, 10000, 10001])]
+    if bed:
+        open(os.path.join(wd, "t.bed"), "w").write("".join("%s\t%d\t%d\n" % b for b in bed)); kw["target"] = os.path.join(wd, "t.bed")
+    if snp:
+        open(os.path.join(wd, "snp.txt"), "w").write("\n".join(snp) + "\n"); kw["snp"] = os.path.join(wd, "snp.txt")
+    if var:
+        open(os.path.join(wd, "v.txt"), "w").write("\n".join(var) + "\n"); kw["variation"] = os.path.join(wd, "v.txt")
+    if ab:
+        open(os.path.join(wd, "ab.txt"), "w").write(ab); kw["abundance"] = os.path.join(wd, "ab.txt")
+    return dict(dir=wd, kw=kw, seed=seed, name="input%d" % seed), kind
+
+
 def run_reference_philox(scn, tag="ref"):
     """Runs the instrumented reference; returns (list of plan paths, sorted list of fastq paths)."""
     d = scn["dir"]

@@ -138,12 +138,13 @@ def test_host_plan_equals_the_instrumented_reference_on_random_jobs(seed, built,
         assert open(a, "rb").read() == open(b, "rb").read(), (seed, mode)
 
 
-@pytest.mark.parametrize("seed", [0, 1, 3, 5, 6, 7, 14, 17, 53])
-def test_host_plan_equals_the_instrumented_reference_on_edge_case_variations(seed, built, workdir):
-    """One seed per kind of helpers.build_edge_variation_scenario (53: an input both programs reject with the same message)."""
+@pytest.mark.parametrize("gen,seed", [("variation", s) for s in (0, 1, 3, 5, 6, 7, 14, 17, 53)] + [("input", s) for s in range(16)])
+def test_host_plan_equals_the_instrumented_reference_on_edge_case_inputs(gen, seed, built, workdir):
+    """One seed per kind of helpers.build_edge_variation_scenario (53: an input both programs reject with the same message) and of
+    helpers.build_edge_input_scenario (capture targets, SNP files, abundance files)."""
     if not os.path.exists(paths.REF_PHILOX):
         pytest.skip("oracle/_ref/simuReads_philox not built (needs /root/reference)")
-    scn, kind = helpers.build_edge_variation_scenario(seed, workdir)
+    scn, kind = (helpers.build_edge_variation_scenario if gen == "variation" else helpers.build_edge_input_scenario)(seed, workdir)
     d = scn["dir"]
 
     def run(binary, tag):
