@@ -209,6 +209,13 @@ int ssc_sub_lookup_host(const double* cdf4, uint32_t u);
  * packing.  Returns the member size, or -1.  Tests inflate it with zlib. */
 int64_t ssc_gzip_member_host(const uint8_t* in, uint32_t n, const uint8_t* sample, size_t sample_n, uint8_t* out, size_t cap);
 
+/* Measurement aid (no reference counterpart): the instruction-issue ceiling of the generation kernel on this GPU.
+ * mode 0 = Philox4x32-10 only, one block per lane-cycle in the generation kernel's launch shape (the cost of the reference's
+ * four uniform draws per base, Profile.cpp:1560/1569/1534/1578, and nothing else); mode 1 = the same plus the per-base table
+ * work and byte stores of an indel-free read on synthetic tables.  Runs `reps` launches over n_pairs pairs of read_length
+ * cycles per mate and returns the mean CUDA-event time of a launch.  bench.py reports it as roofline.issue. */
+int ssc_issue_floor(ssc_handle* h, int mode, int read_length, int64_t n_pairs, int reps, double* ms_per_launch);
+
 int ssc_get_stats(ssc_handle* h, ssc_stats* out);
 int ssc_reset_stats(ssc_handle* h);
 

@@ -15,7 +15,7 @@ from simuscop_b200.paths import ORACLE_LIB
 class OraclePlan(C.Structure):
     _fields_ = [("prof", C.POINTER(abi.ProfileTables)), ("genome", C.c_void_p), ("genome_len", C.c_uint64),
                 ("bins", C.c_void_p), ("n_bins", C.c_int64), ("segs", C.c_void_p), ("n_segs", C.c_int64),
-                ("names", C.c_char_p)]
+                ("names", C.c_char_p), ("genome_first", C.c_uint64)]
 
 
 _lib = None
@@ -48,19 +48,22 @@ def philox(ctr, key):
     return o
 
 
-def generate(plan, seed, pair_lo=0, pair_hi=None, trace=False):
-    """Run the oracle over a simuscop_b200.planfile.Plan. Returns (fq1, fq2, info)."""
+def generate(plan, seed, pair_lo=0, pair_hi=None, trace=False, genome=None, genome_first=0):
+    """Run the oracle over a simuscop_b200.planfile.Plan. Returns (fq1, fq2, info).
+    genome / genome_first: a window of the haplotype store (ASCII, store index of its first base) instead of plan.genome,
+    for plans whose store is too large to hold as ASCII (bench-scale parity tests)."""
     L = lib()
     if pair_hi is None:
         pair_hi = plan.planned_pairs()
     prof = plan.profile_struct()
     op = OraclePlan()
     op.prof = C.pointer(prof)
-    genome = np.ascontiguousarray(plan.genome)
+    genome = np.ascontiguousarray(plan.genome if genome is None else genome)
     bins = np.ascontiguousarray(plan.bins)
     segs = np.ascontiguousarray(plan.segs)
     op.genome = genome.ctypes.data
     op.genome_len = genome.size
+    op.genome_first = int(genome_first)
     op.bins = bins.ctypes.data
     op.n_bins = bins.size
     op.segs = segs.ctypes.data
@@ -76,6 +79,8 @@ def generate(plan, seed, pair_lo=0, pair_hi=None, trace=False):
     n = L.ssco_generate(C.byref(op), seed, pair_lo, pair_hi, out1.ctypes.data, out1.size, C.byref(l1),
                         out2.ctypes.data if plan.paired else None, out2.size if plan.paired else 0, C.byref(l2),
                         tr.ctypes.data if trace else None, npairs if trace else 0, C.byref(nb))
+    if n == -3:
+        raise RuntimeError("oracle: a fragment lies outside the genome window handed over")
     if n < 0:
         raise RuntimeError("oracle output buffer too small (%d)" % n)
     info = dict(emitted=int(n), bases=int(nb.value), trace=tr[:n] if trace else None)

@@ -168,7 +168,7 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 			}
 		if (h->d_slots[0]) cudaFree(h->d_slots[0]);
 		h->d_slots[0] = h->d_slots[1] = nullptr;
-		h->slabPairs = pairs; h->slabCap = cap;
+		h->slabPairs = 0; h->slabCap = 0;          // committed below, once every allocation has succeeded
 		// one scratch, file 2's blobs behind file 1's: the kernel addresses both from one base pointer with 32-bit cursors
 		CK(cudaMalloc((void**)&h->d_slots[0], ((size_t)pairs * FG_SLOT + 256) * nFiles));
 		h->d_slots[1] = nFiles == 2 ? h->d_slots[0] + ((size_t)pairs * FG_SLOT + 256) : nullptr;
@@ -182,6 +182,7 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 			CK(h->d_tileState[b].alloc(nTiles));
 			CK(h->d_ticket[b].alloc(1));
 		}
+		h->slabPairs = pairs; h->slabCap = cap;
 	}
 	if (h->gzip && !h->d_gzBlobs[0]) {
 		for (int f = 0; f < 2; f++) CK(cudaMalloc((void**)&h->d_gzBlobs[f], (size_t)h->slabPairs * FG_SLOT + 64));
@@ -326,17 +327,7 @@ extern "C" {
 const char* ssc_last_error(void) { return g_err.c_str(); }
 int ssc_version(void) { return 1; }
 
-int ssc_create(int device, ssc_handle** out) {
-	if (!out) return fail(SSC_ERR_INVALID, "out is null");
-	*out = nullptr;
-	int count = 0;
-	cudaError_t e = cudaGetDeviceCount(&count);
-	if (e != cudaSuccess || count == 0)
-		return fail(SSC_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
-		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-	if (device < 0 || device >= count) return fail(SSC_ERR_INVALID, "device %d out of range (%d devices)", device, count);
-	CK(cudaSetDevice(device));
-	ssc_handle* h = new ssc_handle();
+static int init_handle(ssc_handle* h, int device) {
 	h->device = device;
 	memset(&h->stats, 0, sizeof(h->stats));
 	cudaDeviceProp prop;
@@ -356,6 +347,22 @@ int ssc_create(int device, ssc_handle** out) {
 		CK(cudaMalloc((void**)&h->d_result[i], sizeof(ssc::BatchResult)));
 		CK(cudaMallocHost((void**)&h->h_result[i], sizeof(ssc::BatchResult)));
 	}
+	return SSC_OK;
+}
+
+int ssc_create(int device, ssc_handle** out) {
+	if (!out) return fail(SSC_ERR_INVALID, "out is null");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(SSC_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0 || device >= count) return fail(SSC_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+	CK(cudaSetDevice(device));
+	ssc_handle* h = new ssc_handle();
+	const int rc = init_handle(h, device);
+	if (rc) { const std::string msg = g_err; ssc_destroy(h); g_err = msg; return rc; }   // nothing of a half-built handle leaks
 	*out = h;
 	return SSC_OK;
 }
@@ -674,6 +681,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 			bool risky = (int64_t)b.epos > b.contig_end - b.hap_base - RL;
 			if (!paired && ((int64_t)b.epos - b.spos + 1) < RL) risky = true;
 			if (paired && t.nIsize == 0 && t.fixedInsert < RL) risky = true;
+			if (paired && t.nIsize > 0 && t.minIS < RL) risky = true;          // an insert-size table that reaches below the read length
 			if (risky) {
 				ssc::CensusBin c;
 				c.hap_base = b.hap_base + SSC_GPAD; c.contig_end = b.contig_end + SSC_GPAD; c.plan_base = pb[i];
@@ -889,6 +897,36 @@ int64_t ssc_gzip_member_host(const uint8_t* in, uint32_t n, const uint8_t* sampl
 	const char* err = ssc::gz_build_tables(hist, &tab);
 	if (err[0]) { fail(SSC_ERR_INVALID, "gzip tables: %s", err); return -1; }
 	return (int64_t)ssc::gz_member_host(&tab, in, n, out, cap);
+}
+
+int ssc_issue_floor(ssc_handle* h, int mode, int read_length, int64_t n_pairs, int reps, double* ms_per_launch) {
+	if (!h || !ms_per_launch) return fail(SSC_ERR_INVALID, "null argument");
+	if (mode < 0 || mode > 1 || read_length < 33 || read_length > 160 || n_pairs < FG_CHUNK || n_pairs > (1 << 22) || reps < 1)
+		return fail(SSC_ERR_INVALID, "ssc_issue_floor: mode 0/1, read_length 33..160, n_pairs 32..4194304, reps >= 1");
+	CK(cudaSetDevice(h->device));
+	const int64_t nTiles = (n_pairs + FG_CHUNK - 1) / FG_CHUNK;
+	const uint32_t blobPitch = FG_CHUNK * FG_SLOT;
+	DevBuf<uint32_t> scratch; DevBuf<uint8_t> blobs;
+	CK(scratch.alloc(1 + (size_t)h->smCount * FG_WORKERS));
+	const size_t fileBytes = (size_t)nTiles * blobPitch + 256;
+	if (mode == 1) {
+		if (2 * fileBytes >= (1ull << 32)) return fail(SSC_ERR_INVALID, "ssc_issue_floor: n_pairs too large for 32-bit blob cursors");
+		CK(blobs.alloc(2 * fileBytes));
+	}
+	cudaStream_t s = h->compute;
+	const int grid = (int)std::min<int64_t>((nTiles + FG_WORKERS - 1) / FG_WORKERS, h->smCount);
+	CK(ssc::launch_issue_floor(mode, read_length, n_pairs, h->seed, grid, scratch.p, blobs.p, blobPitch, (uint32_t)fileBytes, s));   // warm-up
+	CK(cudaEventRecord(h->evStart, s));
+	for (int r = 0; r < reps; r++)
+		CK(ssc::launch_issue_floor(mode, read_length, n_pairs, h->seed + 1 + (uint64_t)r, grid, scratch.p, blobs.p, blobPitch, (uint32_t)fileBytes, s));
+	CK(cudaEventRecord(h->evStop, s));
+	CK(cudaEventSynchronize(h->evStop));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, h->evStart, h->evStop));
+	*ms_per_launch = (double)ms / reps;
+	h->stats.launches += (uint64_t)reps + 1;
+	scratch.release(); blobs.release();
+	return SSC_OK;
 }
 
 int ssc_get_stats(ssc_handle* h, ssc_stats* out) {

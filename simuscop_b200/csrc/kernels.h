@@ -38,6 +38,8 @@ bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemB
 int fast_choose_qbins(int B, int RL);
 cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
                                  cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool pass2);
+cudaError_t launch_issue_floor(int mode, int RL, int64_t nPairs, uint64_t seed, int grid, uint32_t* scratch, uint8_t* blobs,
+                               uint32_t blobPitch, uint32_t file2Off, cudaStream_t stream);   // floor.cu
 cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, uint32_t* hap2, uint32_t* hapN,
                         const int8_t* lut, cudaStream_t stream);

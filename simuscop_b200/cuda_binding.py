@@ -12,7 +12,7 @@ from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
            "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
-           "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host"]
+           "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host", "ssc_issue_floor"]
 
 _lib = None
 
@@ -49,6 +49,7 @@ def lib():
         L.ssc_sub_lookup_host.argtypes = [C.c_void_p, C.c_uint32]
         L.ssc_gzip_member_host.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ssc_gzip_member_host.restype = C.c_int64
+        L.ssc_issue_floor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -144,6 +145,12 @@ class Generator:
         b1, b2, nb, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
         _ck(lib().ssc_generate_device(self.h, lo, hi, C.byref(b1), C.byref(b2), C.byref(nb), C.byref(ms)))
         return dict(bytes1=b1.value, bytes2=b2.value, bases=nb.value, device_ms=ms.value)
+
+    def issue_floor(self, mode, read_length, n_pairs, reps=3):
+        """Mean launch time (ms) of the issue-rate microbenchmark (ssc_issue_floor)."""
+        ms = C.c_double()
+        _ck(lib().ssc_issue_floor(self.h, mode, read_length, n_pairs, reps, C.byref(ms)))
+        return ms.value
 
     def stats(self):
         s = abi.Stats()

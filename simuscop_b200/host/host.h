@@ -41,7 +41,11 @@ public:
 	long length(const std::string& chr) const;               // 0 when unknown
 	// upper-cased bases [start, start+len) of chr (Genome::getSubSequence, lib/genome/Genome.cpp:423-429)
 	const std::string& chromosome(const std::string& chr);   // whole chromosome, cached one at a time
+	// positions of the cached chromosome that hold neither ACGT nor N (IUPAC codes): calculateGCPercent
+	// (lib/mydefine/MyDefine.cpp:279-303) counts only a literal 'N' as unknown, the device mask every non-ACGT character
+	bool other_in(size_t a, size_t b) const;
 private:
+	std::vector<size_t> cachedOther_;
 	std::string path_;
 	std::map<std::string, FastaEntry> idx_;
 	std::string cachedName_, cached_;

@@ -173,6 +173,12 @@ void Fasta::open(const std::string& path) {
 	}
 }
 
+// any character other than A, C, G, T, N in bases [a, b) of the cached chromosome
+bool Fasta::other_in(size_t a, size_t b) const {
+	auto it = std::lower_bound(cachedOther_.begin(), cachedOther_.end(), a);
+	return it != cachedOther_.end() && *it < b;
+}
+
 long Fasta::length(const std::string& chr) const {
 	auto it = idx_.find(chr);
 	return it == idx_.end() ? 0 : it->second.length;
@@ -192,6 +198,7 @@ const std::string& Fasta::chromosome(const std::string& chr) {
 	size_t got = fread(&buf[0], 1, raw, f);
 	fclose(f);
 	cached_.assign((size_t)e.length, 'N');
+	cachedOther_.clear();
 	size_t w = 0, i = 0;
 	while (i < got && w < (size_t)e.length) {
 		const char* nlp = (const char*)memchr(buf.data() + i, '\n', got - i);
@@ -199,10 +206,18 @@ const std::string& Fasta::chromosome(const std::string& chr) {
 		size_t n = std::min(lineEnd - i, (size_t)e.length - w);
 		char* dst = &cached_[w];
 		const unsigned char* src = (const unsigned char*)buf.data() + i;
+		unsigned other = 0;
 		for (size_t k = 0; k < n; k++) {                       // toupper without a table: the loop vectorises
 			const unsigned char c = src[k];
-			dst[k] = (char)(c - (unsigned char)(((unsigned char)(c - 'a') < 26u) << 5));
+			const unsigned char u = (unsigned char)(c - (unsigned char)(((unsigned char)(c - 'a') < 26u) << 5));
+			dst[k] = (char)u;
+			other |= !((u == 'A') | (u == 'C') | (u == 'G') | (u == 'T') | (u == 'N'));
 		}
+		if (other)                                             // rare (IUPAC codes): remember where, see Fasta::other_in
+			for (size_t k = 0; k < n; k++) {
+				const char u = dst[k];
+				if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'N')) cachedOther_.push_back(w + k);
+			}
 		w += n;
 		i = lineEnd + 1;
 	}

@@ -222,6 +222,8 @@ static int gc_percent(const char* s, size_t n) {
 	return 100 * gc / (int)(n - nn);
 }
 
+static inline bool is_acgtn(char ch) { const char c = (char)(ch & 0xDF); return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N'; }   // either case: haplotypes are upper-cased last (Segment.cpp:448-458)
+
 namespace {
 // phase timers of the plan construction (printed when SIMUSCOP_TIMING is set)
 struct PhaseTimers {
@@ -378,21 +380,33 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		std::vector<std::vector<std::string>> haps(v.size());
 		std::vector<std::vector<int>> reps(v.size());
 		std::vector<std::vector<Poke>> pokes(v.size());
-		std::vector<char> onDev(v.size(), 0);
+		std::vector<char> onDev(v.size(), 0), hostGc(v.size(), 0);
 		std::vector<size_t> refOffs(v.size(), 0), refLens(v.size(), 0);
 		bool anyDev = false;
 		for (size_t k = 0; k < v.size(); k++) {
 			const size_t refOff = (size_t)(v[k].start - 1);
 			const size_t refLen = std::min((size_t)v[k].refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
 			refOffs[k] = refOff; refLens[k] = refLen;
-			if (useRefBuild && refLen > 0 && segment_is_copy_only(v[k], popu)) {
+			// The device census counts every non-ACGT character as unknown; the reference only a literal 'N'
+			// (calculateGCPercent, MyDefine.cpp:279-303).  A segment whose haplotypes can hold any other character (IUPAC
+			// codes in the FASTA, in an inserted sequence or in an allele) keeps its strings on the host and gets its GC
+			// percentages from gc_percent() below.
+			bool exotic = fasta.other_in(refOff, refOff + refLen);
+			if (!exotic && useRefBuild && refLen > 0 && segment_is_copy_only(v[k], popu)) {
 				segment_copies_and_pokes(v[k], popu, reps[k], pokes[k]);
-				for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = refLen * (size_t)reps[k][h];
-				onDev[k] = 1; anyDev = true;
-			} else {
-				build_haplotypes(v[k], popu, haps[k]);
-				for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = haps[k][h].size();
+				for (const Poke& pk : pokes[k]) exotic |= !is_acgtn(pk.c);
+				if (!exotic) {
+					for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = refLen * (size_t)reps[k][h];
+					onDev[k] = 1; anyDev = true;
+					continue;
+				}
 			}
+			build_haplotypes(v[k], popu, haps[k]);
+			for (int h = 0; h < ploidy; h++) {
+				L.hapLen[k][h] = haps[k][h].size();
+				if (!exotic) for (char c : haps[k][h]) if (!is_acgtn(c)) { exotic = true; break; }
+			}
+			hostGc[k] = exotic ? 1 : 0;
 		}
 		double t1 = PhaseTimers::now();
 		if (anyDev)
@@ -423,7 +437,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 			for (auto& kv : last) { pokePos.push_back(kv.first); pokeChr.push_back(kv.second); }
 			for (ssc_handle* dev : devs) { rc = ssc_genome_poke(dev, pokePos.data(), pokeChr.data(), (int64_t)pokePos.size()); if (rc) return rc; }
 		}
-		haps.clear(); haps.shrink_to_fit();
+		for (size_t k = 0; k < v.size(); k++) if (!hostGc[k]) { haps[k].clear(); haps[k].shrink_to_fit(); }
 		double t2 = PhaseTimers::now();
 		// census of every bin of the chromosome in one call
 		std::vector<std::vector<BinSpec>> specs(v.size());
@@ -431,6 +445,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		for (size_t k = 0; k < v.size(); k++) {
 			if (v[k].weighted) continue;
 			enumerate_bins(v[k], L.hapLen[k], specs[k]);
+			if (hostGc[k]) continue;
 			for (auto& sp : specs[k]) {
 				if (sp.kind == 2) continue;
 				starts.push_back(L.base[k][sp.hap] + sp.gcStart);
@@ -449,6 +464,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 			gc.assign(specs[k].size(), 0);
 			for (size_t b = 0; b < specs[k].size(); b++) {
 				if (specs[k][b].kind == 2) continue;
+				if (hostGc[k]) { gc[b] = gc_percent(haps[k][specs[k][b].hap].data() + specs[k][b].gcStart, (size_t)specs[k][b].gcLen); continue; }
 				// calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303: empty -> 0, any N -> -1, else 100*gc/n (integer)
 				const int32_t n = lens[q];
 				gc[b] = n == 0 ? 0 : (cnn[q] > 0 ? -1 : 100 * cgc[q] / n);
@@ -555,6 +571,9 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 	}
 
 	PlanWriter pw;
+	// "<path>.flat": profile tables + the flat bin / segment / name arrays handed to ssc_set_plan, no haplotype strings
+	// (tags 5-7; a full dump of a 3 Gb diploid job would carry 6 GB of ASCII)
+	const bool flatDump = dumpPath.size() > 5 && dumpPath.compare(dumpPath.size() - 5, 5, ".flat") == 0;
 	if (!dumpPath.empty()) {
 		pw.fp = fopen(dumpPath.c_str(), "wb");
 		if (!pw.fp) die(3, "cannot open " + dumpPath);
@@ -600,7 +619,7 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 			names += nm;
 			// the chromosome's haplotype strings (Genome.cpp:876-878): needed here in plan-only mode and for a plan dump
 			std::vector<std::vector<std::string>> haps(v.size());
-			if (!onDevice || pw.fp) {
+			if (!onDevice || (pw.fp && !flatDump)) {
 				for (size_t k = 0; k < v.size(); k++) {
 					if (!v[k].hapCache.empty()) {     // kept from the weights pass (same strings: generateSegSequences is deterministic once mIndx is set)
 						size_t bb = 0;
@@ -611,7 +630,7 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 					} else build_haplotypes(v[k], popu, haps[k]);
 				}
 			}
-			if (pw.fp) {
+			if (pw.fp && !flatDump) {
 				std::string u;
 				PlanWriter::app<int32_t>(u, (int32_t)popu.size()); PlanWriter::app<int32_t>(u, (int32_t)chr.size());
 				u += popu; u += chr;
@@ -656,7 +675,7 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 					bins.push_back(sb);
 				}
 				segments.push_back(ss);
-				if (pw.fp) {
+				if (pw.fp && !flatDump) {
 					std::string r;
 					PlanWriter::app<int32_t>(r, sg.idx); PlanWriter::app<int32_t>(r, sg.CN);
 					PlanWriter::app<int64_t>(r, sg.start); PlanWriter::app<int64_t>(r, sg.end);
@@ -676,6 +695,11 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 	if (getenv("SIMUSCOP_TIMING"))
 		fprintf(stderr, "[simuscop timing] haplotypes %.2f s, upload+pack %.2f s, gc census (device, incl. bin enumeration %.2f s) %.2f s, gc weights (host) %.2f s, read counts %.2f s\n",
 		        g_tm.build, g_tm.upload, g_tm.enumerate, g_tm.census, g_tm.gc, g_tm.counts);
+	if (pw.fp && flatDump) {
+		pw.rec(5, std::string((const char*)bins.data(), bins.size() * sizeof(ssc_bin)));
+		pw.rec(6, std::string((const char*)segments.data(), segments.size() * sizeof(ssc_segment)));
+		pw.rec(7, names);
+	}
 	if (pw.fp) { pw.rec(9, std::string()); fclose(pw.fp); }
 	if (devs.empty()) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
 	for (ssc_handle* dev : devs) {

@@ -119,11 +119,18 @@ def read_plan(path):
             cur["segs"].append(dict(segIndx=segIndx, CN=CN, start=start, end=end, segsize=segsize,
                                     readCount=readCount, hapLen=hapLen, haps=haps, spos=spos, epos=epos,
                                     hap=hap, rc=rc))
+        elif tag == 5:        # flat dump ("<path>.flat"): the ssc_bin / ssc_segment / name arrays themselves, no haplotypes
+            plan.bins = np.frombuffer(body, dtype=abi.BIN_DTYPE).copy()
+        elif tag == 6:
+            plan.segs = np.frombuffer(body, dtype=abi.SEG_DTYPE).copy()
+        elif tag == 7:
+            plan.names = bytes(body)
         elif tag == 9:
             break
         else:
             raise ValueError("unknown plan record tag %d" % tag)
-    _flatten(plan, units)
+    if plan.bins is None:
+        _flatten(plan, units)
     return plan
 
 

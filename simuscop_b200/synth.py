@@ -8,8 +8,13 @@ import numpy as np
 _LUT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def random_bases(rng, n, n_runs=0, lower_runs=0, run_len=500):
+def random_bases(rng, n, n_runs=0, lower_runs=0, run_len=500, iupac=0):
     seq = _LUT[rng.integers(0, 4, size=n, dtype=np.uint8)]
+    if iupac:
+        # IUPAC ambiguity codes as hg19 / hg38 carry them: neither ACGT nor N (drawn first so that the other options
+        # leave the random stream of existing fixtures untouched when iupac == 0)
+        pos = rng.integers(0, n, size=iupac)
+        seq[pos] = np.frombuffer(b"RYKMSWrymk", dtype=np.uint8)[rng.integers(0, 10, size=iupac)]
     for _ in range(n_runs):
         s = int(rng.integers(0, max(1, n - run_len)))
         seq[s:s + run_len] = ord("N")
@@ -35,12 +40,12 @@ def write_fasta(path, chroms, line=60):
                 f.write(seq[full * line:].tobytes() + b"\n")
 
 
-def make_genome(path, lengths, seed=20, names=None, n_runs=0, lower_runs=0, run_len=500):
+def make_genome(path, lengths, seed=20, names=None, n_runs=0, lower_runs=0, run_len=500, iupac=0):
     rng = np.random.default_rng(seed)
     chroms = []
     for i, n in enumerate(lengths):
         name = names[i] if names else "chr%d" % (i + 1)
-        chroms.append((name, random_bases(rng, n, n_runs, lower_runs, run_len)))
+        chroms.append((name, random_bases(rng, n, n_runs, lower_runs, run_len, iupac)))
     write_fasta(path, chroms)
     return chroms
 

@@ -30,6 +30,14 @@ SCENARIOS = {
 SCENARIOS["pe_ploidy3"] = dict(lengths=[2600000], names=["chr20"], profile="XTen", layout="PE", coverage=2, insertSize=300,
                                variation=True, ploidy=3, n_runs=1)
 SCENARIOS["se_ploidy1"] = dict(lengths=[700000, 300000], profile="HiSeq2500", layout="SE", coverage=3, insertSize=200, ploidy=1)
+# IUPAC ambiguity codes in the FASTA, in an inserted sequence and in an SNV allele: they behave as N on the read path but are
+# ordinary non-GC bases for the GC weights (calculateGCPercent counts only a literal 'N', MyDefine.cpp:279-303)
+SCENARIOS["pe_iupac"] = dict(lengths=[260000, 90000], names=["chr20", "chr21"], profile="XTen", layout="PE", coverage=3,
+                             insertSize=300, n_runs=1, lower_runs=1, iupac=60, variation_text=(
+                                 "i\ttest\tchr20\t45010\ttcgrytcg\thomo\n"
+                                 "s\ttest\tchr20\t50010\tA\tY\thet\n"
+                                 "d\ttest\tchr20\t120010\t8\thomo\n"
+                                 "c\ttest\tchr20\t150001\t200000\t3\t2\n"))
 SCENARIOS["se_mini"] = dict(lengths=[30000], profile="GAIIx", layout="SE", coverage=2, insertSize=250, n_runs=1)
 
 # synthetic profiles (simuscop_b200.synth.write_profile): odd k-mer sizes, short / long reads, heavy indel rates,
@@ -107,12 +115,16 @@ def build_scenario(name, workdir, seed=7):
     os.makedirs(d, exist_ok=True)
     data = testdata.materialize(os.path.join(workdir, "data"))
     synth.make_genome(os.path.join(d, "ref.fa"), sc["lengths"], seed=20, names=sc.get("names"),
-                      n_runs=sc.get("n_runs", 0), lower_runs=sc.get("lower_runs", 0), run_len=300)
+                      n_runs=sc.get("n_runs", 0), lower_runs=sc.get("lower_runs", 0), run_len=300, iupac=sc.get("iupac", 0))
     kw = dict(ref=os.path.join(d, "ref.fa"), profile=os.path.join(data, testdata.PROFILES[sc["profile"]]),
               layout=sc["layout"], coverage=sc["coverage"], insertSize=sc["insertSize"], threads=1, verbose=0,
               name="test")
     if sc.get("ploidy"):
         kw["ploidy"] = sc["ploidy"]
+    if sc.get("variation_text"):
+        with open(os.path.join(d, "variations.txt"), "w") as f:
+            f.write(sc["variation_text"])
+        kw["variation"] = os.path.join(d, "variations.txt")
     if sc.get("variation"):
         with open(os.path.join(d, "variations.txt"), "w") as f:
             f.write(VARIATION_SMALL)
@@ -452,3 +464,154 @@ def first_diff(a, b):
         if a[i] != b[i]:
             return i
     return n if len(a) != len(b) else -1
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's three shipped test configurations (configFiles/config_test_{wgs,wes,tumor}.txt), key for key and value for
+# value, run from a directory laid out like the reference's checkout (./testData/..., ./results).  testData/ref.fa.gz is a
+# missing blob upstream: a seeded synthetic chr20 of hg19's length (63 025 520 bp, covers every coordinate of
+# variations*.txt / snp.txt / exon_regions.bed) with N runs and lower-case stretches stands in for it.
+# ---------------------------------------------------------------------------------------------
+SHIPPED = {
+    "wgs": dict(ref="./testData/ref.fa.gz", profile="./testData/Illumina_GenomeAnalyzerIIx.profile",
+                variation="./testData/variations.txt", snp="./testData/snp.txt", name="test", output="./results",
+                layout="PE", threads=4, verbose=1, coverage=10, insertSize=250),
+    "wes": dict(ref="./testData/ref.fa.gz", profile="./testData/Illumina_HiSeq2500.profile",
+                variation="./testData/variations.txt", snp="./testData/snp.txt", target="./testData/exon_regions.bed",
+                name="test", output="./results", layout="PE", threads=2, verbose=1, coverage=100, insertSize=200),
+    "tumor": dict(ref="./testData/ref.fa.gz", profile="./testData/Illumina_GenomeAnalyzerIIx.profile",
+                  variation="./testData/variations_tumor.txt", snp="./testData/snp.txt", name="clone1, clone2, clone3, normal",
+                  abundance="./testData/abundance_tumor.txt", output="./results", layout="SE", threads=4, verbose=1,
+                  coverage=10, insertSize=200),
+}
+SHIPPED_SEED = 7
+SHIPPED_CHR20 = 63025520
+
+
+def build_shipped_tree(workdir):
+    """<workdir>/shipped/{testData,configFiles}: the data files of data/, the synthetic ref.fa.gz and the three configs."""
+    import gzip
+    import shutil
+    root = os.path.join(workdir, "shipped")
+    td = os.path.join(root, "testData")
+    os.makedirs(os.path.join(root, "configFiles"), exist_ok=True)
+    testdata.materialize(td)
+    gz = os.path.join(td, "ref.fa.gz")
+    if not os.path.exists(gz):
+        fa = os.path.join(td, "ref_synth.fa")
+        synth.make_genome(fa, [SHIPPED_CHR20], seed=20, names=["chr20"], n_runs=6, lower_runs=6, run_len=20000)
+        with open(fa, "rb") as fi, gzip.GzipFile(gz + ".tmp", "wb", compresslevel=1, mtime=0) as fo:
+            shutil.copyfileobj(fi, fo, 1 << 24)
+        os.replace(gz + ".tmp", gz)
+        os.remove(fa)
+    for k, kw in SHIPPED.items():
+        synth.write_config(os.path.join(root, "configFiles", "config_test_%s.txt" % k), **kw)
+    return root
+
+
+def run_shipped(binary, root, which, tag, env_extra=None):
+    """Runs `binary configFiles/config_test_<which>.txt` from a private copy of the tree (the programs gunzip the reference
+    next to itself and write ./results); returns {file name: path} of the FASTQ files."""
+    import shutil
+    run = os.path.join(root, "run_%s_%s" % (which, tag))
+    shutil.rmtree(run, ignore_errors=True)
+    os.makedirs(os.path.join(run, "testData"))
+    for fn in os.listdir(os.path.join(root, "testData")):
+        if fn in ("ref.fa", "ref.fa.fai"):
+            continue
+        src = os.path.join(root, "testData", fn)
+        dst = os.path.join(run, "testData", fn)
+        if fn == "ref.fa.gz":
+            shutil.copyfile(src, dst)          # gunzipped in place by the program
+        else:
+            os.symlink(src, dst)
+    os.makedirs(os.path.join(run, "configFiles"))
+    shutil.copyfile(os.path.join(root, "configFiles", "config_test_%s.txt" % which), os.path.join(run, "configFiles", "config.txt"))
+    env = dict(os.environ, SIMUSCOP_SEED=str(SHIPPED_SEED), **(env_extra or {}))
+    r = subprocess.run([binary, "configFiles/config.txt"], cwd=run, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = os.path.join(run, "results")
+    if not os.path.isdir(res):
+        return {}
+    return {fn: os.path.join(res, fn) for fn in sorted(os.listdir(res))}
+
+
+class FastaStoreWindow:
+    """Windows of the haplotype store of a variant-free job, taken from the FASTA file itself (not from the device): without
+    variations every contig (population, chromosome, haplotype index) is the upper-cased chromosome, and the store is the
+    contigs back to back in plan order -- contig k covers [contig_end[k-1], contig_end[k]).  Used by the bench-scale parity
+    tests, whose 6-Gbase store is too large to hold as ASCII."""
+
+    def __init__(self, plan, fasta_path):
+        import numpy as np
+        self.np = np
+        self.fd = os.open(fasta_path, os.O_RDONLY)          # pread: safe to share with forked oracle workers
+        fai = {}
+        with open(fasta_path + ".fai") as f:
+            for line in f:
+                p = line.rstrip("\n").split("\t")
+                name = p[0].split()[0]
+                for pre in ("chrom", "chr"):
+                    if name.startswith(pre):
+                        name = name[len(pre):]
+                        break
+                fai[name] = (int(p[1]), int(p[2]), int(p[3]), int(p[4]))
+        ends, chroms = [], []
+        segs, bins, names = plan.segs, plan.bins, plan.names
+        for s in range(len(segs)):
+            nb = int(segs["n_bins"][s])
+            if nb == 0:
+                continue
+            b = bins[int(segs["first_bin"][s]):int(segs["first_bin"][s]) + nb]
+            b = b[b["read_count"] > 0]
+            nm = names[int(segs["name_offset"][s]):int(segs["name_offset"][s]) + int(segs["name_len"][s])].decode()
+            chrom = nm.split("#")[1]
+            for ce in np.unique(b["contig_end"]):
+                ends.append(int(ce)); chroms.append(chrom)
+        order = sorted(set(zip(ends, chroms)))
+        self.ends = [e for e, _ in order]
+        self.chroms = [c for _, c in order]
+        self.starts = [0] + self.ends[:-1]
+        for st, en, c in zip(self.starts, self.ends, self.chroms):
+            assert en - st == fai[c][0], "contig of %s is not the plain chromosome (%d vs %d bases)" % (c, en - st, fai[c][0])
+        self.fai = fai
+
+    def _chrom_slice(self, chrom, a, b):
+        np = self.np
+        length, off, lb, lw = self.fai[chrom]
+        fa0 = off + (a // lb) * lw + a % lb
+        fa1 = off + ((b - 1) // lb) * lw + (b - 1) % lb + 1
+        raw = np.frombuffer(os.pread(self.fd, fa1 - fa0, fa0), np.uint8)
+        seq = raw[raw != 10]
+        assert len(seq) == b - a
+        return np.where((seq >= 97) & (seq <= 122), seq - 32, seq).astype(np.uint8)
+
+    def window(self, lo, hi):
+        """ASCII store bases [lo, hi) (clipped to the store)."""
+        import bisect
+        np = self.np
+        lo = max(0, lo); hi = min(hi, self.ends[-1])
+        parts = []
+        k = bisect.bisect_right(self.ends, lo)
+        while lo < hi:
+            st, en = self.starts[k], self.ends[k]
+            b = min(hi, en)
+            parts.append(self._chrom_slice(self.chroms[k], lo - st, b - st))
+            lo = b; k += 1
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def pair_window(plan, pair_lo, pair_hi, slack=4096):
+    """Store interval [lo, hi) that planned pairs [pair_lo, pair_hi) can touch: their bins' start ranges plus `slack` bases
+    (longest fragment), and the bin index range."""
+    import numpy as np
+    rc = np.maximum(plan.bins["read_count"].astype(np.int64), 0)
+    per = (rc + 1) // 2 if plan.paired else rc
+    base = np.concatenate(([0], np.cumsum(per)))
+    b0 = int(np.searchsorted(base, pair_lo, side="right") - 1)
+    b1 = int(np.searchsorted(base, pair_hi, side="left"))
+    b = plan.bins[b0:b1]
+    b = b[per[b0:b1] > 0]
+    lo = int((b["hap_base"] + b["spos"]).min())
+    hi = int(np.minimum(b["hap_base"] + b["epos"] + slack, b["contig_end"]).max())
+    return lo, hi, b0, b1

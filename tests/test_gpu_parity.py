@@ -16,7 +16,7 @@ def gen(built):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor", "pe_ploidy3", "se_ploidy1"])
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor", "pe_ploidy3", "se_ploidy1", "pe_iupac"])
 def test_fastq_bit_exact_vs_instrumented_reference(name, gen, workdir):
     scn = helpers.build_scenario(name, workdir)
     plans, out = helpers.run_reference_philox(scn)
@@ -75,7 +75,7 @@ def test_batching_and_ranges_are_seamless(built, workdir):
         g.close()
 
 
-@pytest.mark.parametrize("name", ["pe_xten", "pe_variants", "pe_wes", "se_tumor", "pe_tiny"])
+@pytest.mark.parametrize("name", ["pe_xten", "pe_variants", "pe_wes", "se_tumor", "pe_tiny", "pe_iupac"])
 def test_cli_end_to_end_matches_instrumented_reference(name, built, workdir):
     """The drop-in `simuReads <config>` (C++ front end -> C ABI -> CUDA) writes the same FASTQ files."""
     import glob
@@ -235,7 +235,7 @@ def test_device_plan_equals_host_plan(built, workdir):
     import os
     import subprocess
     from simuscop_b200 import paths, synth
-    for name in ("pe_variants", "pe_wes", "se_tumor"):
+    for name in ("pe_variants", "pe_wes", "se_tumor", "pe_iupac"):
         scn = helpers.build_scenario(name, workdir)
         d = scn["dir"]
         dumps = {}

@@ -99,7 +99,7 @@ def _plan_only(scn, tag):
     return sorted(glob.glob(os.path.join(d, "plan_%s.*.plan" % tag)), key=lambda p: int(p.split(".")[-2]))
 
 
-@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor", "pe_ploidy3", "se_ploidy1"])
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_variants", "pe_wes", "se_tumor", "pe_ploidy3", "se_ploidy1", "pe_iupac"])
 def test_host_plan_matches_golden_hashes(name, built, workdir):
     """Tables, haplotypes (SNP/SNV/indel/CNV), bins and read counts of the C++ front end, byte for byte."""
     scn = helpers.build_scenario(name, workdir)

@@ -62,7 +62,7 @@ def test_oracle_pair_ranges_concatenate(built, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_PHILOX), reason="instrumented reference binary not built")
-@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_wes", "pe_ploidy3", "se_ploidy1"])
+@pytest.mark.parametrize("name", ["pe_xten", "se_gaiix", "pe_tiny", "pe_wes", "pe_ploidy3", "se_ploidy1", "pe_iupac"])
 def test_oracle_matches_live_instrumented_reference(name, built, workdir):
     scn = helpers.build_scenario(name, workdir)
     plans, out = helpers.run_reference_philox(scn, tag="pin")
@@ -114,3 +114,62 @@ def test_oracle_and_host_on_synthetic_profiles(name, built, workdir):
     r = subprocess.run([paths.SIMUREADS, cfg], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(os.path.join(d, "plan_ours.0.plan"), "rb").read() == open(plans[0], "rb").read()
+
+
+def test_windowed_oracle_and_flat_plan_dump(built, workdir):
+    """The two pieces the bench-scale GPU parity test stands on, checked on a small job against the instrumented reference:
+    (1) the flat dump of the C++ front end (ssc_bin / ssc_segment / name arrays, no haplotype strings) equals the flattened
+    full dump; (2) the oracle run on a pair sub-range with only the window of the store those pairs can touch, cut from the
+    FASTA file, gives exactly the bytes of that range in the reference's files."""
+    import ctypes as C
+    import os
+    import numpy as np
+    from oracle import binding as oracle_binding
+    from simuscop_b200 import host_binding, synth
+    scn = helpers.build_scenario("pe_xten", workdir)
+    plans, out = helpers.run_reference_philox(scn, tag="win")
+    full = planfile.read_plan(plans[0])
+    r1p, r2p = helpers.sample_files(out, full, 0, scn)
+    r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
+    d = scn["dir"]
+    cfg = os.path.join(d, "cfg_flat.txt")
+    synth.write_config(cfg, output=os.path.join(d, "out_flat"), **scn["kw"])
+    job = host_binding.Job(cfg, scn["seed"])
+    flat_path = os.path.join(d, "plan.flat")
+    rc = host_binding.lib().ssh_prepare_sample(job.j, 0, None, flat_path.encode(), C.byref(C.c_int64()), C.byref(C.c_int64()))
+    assert rc == 0
+    job.close()
+    flat = planfile.read_plan(flat_path)
+    assert flat.genome is None
+    assert (flat.bins == full.bins).all() and (flat.segs == full.segs).all() and flat.names == full.names
+    store = helpers.FastaStoreWindow(flat, scn["kw"]["ref"])
+    assert (store.window(0, len(full.genome)) == np.frombuffer(bytes(full.genome), np.uint8)).all()
+    n = flat.planned_pairs()
+    whole1, whole2, _ = oracle_binding.generate(full, scn["seed"])
+    assert (whole1, whole2) == (r1, r2)
+    cuts = [0, 5, n // 3, n // 3 + 700, n - 3, n]
+    got1, got2 = b"", b""
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        wlo, whi, _, _ = helpers.pair_window(flat, a, b)
+        assert whi - wlo < len(full.genome) or b - a > n // 2
+        o1, o2, info = oracle_binding.generate(flat, scn["seed"], a, b, genome=store.window(wlo, whi), genome_first=wlo)
+        got1 += o1; got2 += o2
+    assert (got1, got2) == (r1, r2)
+    with pytest.raises(RuntimeError):      # a window that misses the fragments is an error, never a silent read elsewhere
+        oracle_binding.generate(flat, scn["seed"], 0, 50, genome=store.window(0, 100), genome_first=0)
+
+
+def test_shipped_wes_config_host_plan_and_oracle(built, workdir):
+    """BASELINE.json configs[1] on the CPU side: the reference's shipped config_test_wes.txt (4 677 capture targets at 100x,
+    SNPs + variations, HiSeq2500 PE125, synthetic 63 Mb chr20) through the C++ front end in plan-only mode and the C oracle
+    reproduces the FASTQ files the instrumented reference wrote for it (tests/golden/shipped.json) -- the same files the
+    CUDA CLI must reproduce on the GPU box (tests/test_gpu_shipped_configs.py)."""
+    from simuscop_b200 import paths
+    gold = json.load(open(os.path.join(GOLD, "shipped.json")))["configs"]["wes"]
+    root = helpers.build_shipped_tree(workdir)
+    prefix = os.path.join(workdir, "shipped_wes_plan")
+    helpers.run_shipped(paths.SIMUREADS, root, "wes", "plan", {"SIMUSCOP_PLAN_ONLY": "1", "SIMUSCOP_DUMP_PLAN": prefix})
+    plan = planfile.read_plan(prefix + ".0.plan")
+    o1, o2, _ = oracle_binding.generate(plan, helpers.SHIPPED_SEED)
+    assert len(o1) == gold["test_1.fq"]["bytes"] and hashlib.sha256(o1).hexdigest() == gold["test_1.fq"]["sha256"]
+    assert len(o2) == gold["test_2.fq"]["bytes"] and hashlib.sha256(o2).hexdigest() == gold["test_2.fq"]["sha256"]
