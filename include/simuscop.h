@@ -122,6 +122,7 @@ typedef struct ssc_stats {
 	double   compact_kernel_ms;/* CUDA-event time of the compaction kernel alone (ssc_generate_device) */
 	uint64_t timed_batches;    /* launches covered by gen_kernel_ms */
 	uint64_t gz_bytes;         /* gzip mode: compressed bytes written to the slabs (fastq_bytes stays the plain size) */
+	uint64_t bin_bytes;        /* algorithmic bin-record bytes read: 64 bytes per distinct bin of every generated batch */
 } ssc_stats;
 
 /*
@@ -165,6 +166,13 @@ int ssc_genome_size(ssc_handle* h, uint64_t* n_bases);
  * overwrites single bases (store indices, distinct) with the given characters.  ssc_genome_read decodes store bases
  * back to upper-case ASCII (non-ACGT -> 'N'), a diagnostic for tests. */
 int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n);
+/* The same from the FASTA file itself (FastaReference::getSequence, lib/fastahack/Fasta.cpp:304-334, and the upper-casing
+ * of Genome::getSubSequence done on the device): the sequence lines of one record are read from `fd` (raw_len bytes at
+ * file_offset, straight into pinned staging buffers) and unfolded on the GPU with the geometry of the record's .fai entry
+ * (n_bases bases, line_bases bases per line in line_width bytes).  *n_other receives the number of characters that are
+ * neither ACGT nor N in either case (IUPAC codes). */
+int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
+                               uint32_t line_bases, uint32_t line_width, uint64_t* n_other);
 int ssc_genome_append_ref(ssc_handle* h, uint64_t ref_off, uint64_t len, int32_t reps, uint64_t* first_base);
 int ssc_genome_poke(ssc_handle* h, const int64_t* store_pos, const char* chars, int64_t n);
 int ssc_genome_read(ssc_handle* h, uint64_t start, uint64_t n, char* out);

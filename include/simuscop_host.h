@@ -35,6 +35,14 @@ const char* ssh_output_dir(ssh_job* job);
 /* dump_path may be NULL; otherwise an SSCPLAN1 file of the sample is written there */
 int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_path,
                        int64_t* planned_pairs, int64_t* emitted_pairs);
+/* Output side (the role of SeqWriter, lib/seqwriter/SeqWriter.cpp:41-54): an ordered FASTQ file writer whose sink can be
+ * handed to ssc_generate with user = the writer.  path2 NULL = single-end.  Every slab is cut into chunks that `threads`
+ * workers pwrite() at their final offsets (threads <= 1: written by the caller's thread). */
+typedef struct ssh_writer ssh_writer;
+int ssh_writer_open(const char* path1, const char* path2, int threads, ssh_writer** out);
+ssc_sink_fn ssh_writer_sink(void);
+int ssh_writer_close(ssh_writer* w, uint64_t* bytes1, uint64_t* bytes2);
+
 /* The whole drop-in run: every sample -> FASTQ files in the output directory, on `device`. */
 int ssh_run(ssh_job* job, int device);
 

@@ -2,8 +2,10 @@
 // generation with pinned double-buffered device->host streaming.  No CPU fallback: every
 // entry point needs a CUDA device and fails loudly otherwise.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -92,6 +94,8 @@ struct ssc_handle {
 	DevBuf<uint32_t> d_hap2, d_hapN;
 	uint64_t genomeCap = 0, genomeSize = 0;
 	DevBuf<uint8_t> d_ref;                        // ASCII chromosome for ssc_genome_append_ref
+	DevBuf<uint8_t> d_raw;                        // raw FASTA lines of the chromosome (ssc_reference_upload_fasta), grow-only
+	DevBuf<unsigned long long> d_other;
 	uint64_t refSize = 0;
 	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
 	uint8_t* d_stage[2] = {nullptr, nullptr};
@@ -102,6 +106,7 @@ struct ssc_handle {
 	bool havePlan = false;
 	uint64_t seed = 0;
 	std::vector<int64_t> planBaseAll, emitBaseAll;   // per original bin (+1 sentinel)
+	std::vector<int64_t> devEmitBase;                // per device bin (+1 sentinel): host copy of d_emitBase
 	DevBuf<ssc::DevBin> d_bins;
 	DevBuf<int64_t> d_emitBase;
 	DevBuf<uint16_t> d_risky;
@@ -117,9 +122,13 @@ struct ssc_handle {
 	DevBuf<int32_t> d_tileStart[2];
 	DevBuf<unsigned long long> d_tileState[2];
 	DevBuf<unsigned int> d_ticket[2];
-	uint8_t* d_slots[2] = {nullptr, nullptr};   // pass-1 scratch of the fast kernel (one set, stream ordered)
+	uint8_t* d_slots[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][file] pass-1 blob scratch of the fast kernel; file 2 lies
+	                                                                     // behind file 1 in the same allocation.  Two buffers: the blobs of batch
+	                                                                     // k are moved to their dense slab by the launch that generates batch k+1
 	DevBuf<unsigned int> d_ticket2;
-	DevBuf<unsigned long long> d_blobPrefix;
+	DevBuf<unsigned long long> d_blobPrefix[2];
+	struct { bool valid = false; ssc::GenParams P; } pending;          // generated + scanned, blobs not yet moved
+	cudaEvent_t evDense[2] = {nullptr, nullptr};
 	DevBuf<int64_t> d_cenStarts;                  // ssc_gc_census scratch (grow-only)
 	DevBuf<int32_t> d_cenLens, d_cenGc, d_cenNn;
 	ssc::BatchResult* d_result[2] = {nullptr, nullptr};
@@ -166,15 +175,17 @@ int ensure_batch_resources(ssc_handle* h, bool needHost) {
 				if (h->h_out[b][f]) cudaFreeHost(h->h_out[b][f]);
 				h->d_out[b][f] = nullptr; h->h_out[b][f] = nullptr;
 			}
-		if (h->d_slots[0]) cudaFree(h->d_slots[0]);
-		h->d_slots[0] = h->d_slots[1] = nullptr;
+		for (int b = 0; b < 2; b++) { if (h->d_slots[b][0]) cudaFree(h->d_slots[b][0]); h->d_slots[b][0] = h->d_slots[b][1] = nullptr; }
 		h->slabPairs = 0; h->slabCap = 0;          // committed below, once every allocation has succeeded
-		// one scratch, file 2's blobs behind file 1's: the kernel addresses both from one base pointer with 32-bit cursors
-		CK(cudaMalloc((void**)&h->d_slots[0], ((size_t)pairs * FG_SLOT + 256) * nFiles));
-		h->d_slots[1] = nFiles == 2 ? h->d_slots[0] + ((size_t)pairs * FG_SLOT + 256) : nullptr;
+		h->pending.valid = false;
+		for (int b = 0; b < 2; b++) {
+			// file 2's blobs behind file 1's: the kernel addresses both from one base pointer with 32-bit cursors
+			CK(cudaMalloc((void**)&h->d_slots[b][0], ((size_t)pairs * FG_SLOT + 256) * nFiles));
+			h->d_slots[b][1] = nFiles == 2 ? h->d_slots[b][0] + ((size_t)pairs * FG_SLOT + 256) : nullptr;
+			CK(h->d_blobPrefix[b].alloc((size_t)(pairs / 16) + 2));
+		}
 		for (int f = 0; f < 2; f++) { if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]); h->d_gzBlobs[f] = nullptr; }
 		CK(h->d_ticket2.alloc(1));
-		CK(h->d_blobPrefix.alloc((size_t)(pairs / 16) + 2));
 		int nTiles = (int)(pairs / 16) + 2;   // enough for every kernel's tile size
 		for (int b = 0; b < 2; b++) {
 			for (int f = 0; f < nFiles; f++) CK(cudaMalloc((void**)&h->d_out[b][f], cap));
@@ -233,6 +244,19 @@ int build_gz_tables(ssc_handle* h, const ssc::GenParams& P, int nTiles) {
 	return SSC_OK;
 }
 
+// Moves the blobs of the last launched batch to its dense slab with the stand-alone kernel (the last batch of a call: no
+// later launch carries its moves).
+int flush_pending(ssc_handle* h) {
+	if (!h->pending.valid) return SSC_OK;
+	h->pending.valid = false;
+	CK(ssc::launch_move_blobs(h->pending.P, h->smCount, h->compute));
+	h->stats.launches += 1;
+	return SSC_OK;
+}
+
+// Launches batch [emitLo, emitHi) into buffer set `buf`.  Fast kernel, plain output: pass 1 + the scan of the blob lengths;
+// the blobs are moved to the dense slab d_out[buf] by the next launch_batch (fused into its generation kernel) or by
+// flush_pending.  Every other mode leaves the finished slab in d_out[buf] when its kernels have run.
 int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	int qsmem = 0; size_t fastSmem = 0;
 	const bool fast = use_fast(h, &qsmem, &fastSmem);
@@ -244,7 +268,16 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	CK(cudaMemsetAsync(h->d_ticket2.p, 0, sizeof(unsigned int), s));
 	CK(cudaMemsetAsync(h->d_result[buf], 0, sizeof(ssc::BatchResult), s));
 	CK(ssc::launch_locate(h->d_emitBase.p, h->nDevBins, emitLo, tp, nTiles, h->d_tileStart[buf].p, s));
+	h->stats.launches += 1;
+	{
+		// distinct bins of the batch (statistics: the algorithmic bin-record bytes of the roofline)
+		const std::vector<int64_t>& eb = h->devEmitBase;
+		const size_t bLo = std::upper_bound(eb.begin(), eb.end(), emitLo) - eb.begin() - 1;
+		const size_t bHi = std::lower_bound(eb.begin(), eb.end(), emitHi) - eb.begin();
+		h->stats.bin_bytes += (uint64_t)(bHi > bLo ? bHi - bLo : 0) * sizeof(ssc::DevBin);
+	}
 	ssc::GenParams P;
+	memset(&P, 0, sizeof(P));
 	P.t = h->dt;
 	P.hap2 = h->d_hap2.p; P.hapN = h->d_hapN.p;
 	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
@@ -258,20 +291,18 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 		P.rk[2 * r] = (uint32_t)h->seed + (uint32_t)r * 0x9E3779B9u;
 		P.rk[2 * r + 1] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
 	}
-	P.tileStartBin = h->d_tileStart[buf].p; P.nTiles = nTiles;
-	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p; P.ticket2 = h->d_ticket2.p; P.blobPrefix = h->d_blobPrefix.p;
+	P.tileStartBin = h->d_tileStart[buf].p; P.nTiles = nTiles; P.nLoop = nTiles; P.nTilesPrev = 0;
+	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p; P.ticket2 = h->d_ticket2.p; P.blobPrefix = h->d_blobPrefix[buf].p;
 	P.out1 = h->d_out[buf][0]; P.out2 = h->d_out[buf][1];
 	P.cap1 = h->slabCap; P.cap2 = h->slabCap;
 	P.result = h->d_result[buf];
 	int grid = std::min(nTiles, h->smCount);
 	if (fast) {
-		grid = std::min((nTiles + FG_GEN - 1) / FG_GEN, h->smCount);
-		if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
 		// pass 1 writes one blob per ticket and file into the scratch, pass 2 (scan of the blob lengths + one move per blob) the dense slab
 		P.dense1 = P.out1; P.dense2 = P.out2;
-		P.out1 = h->d_slots[0]; P.out2 = h->d_slots[1];
+		P.out1 = h->d_slots[buf][0]; P.out2 = h->d_slots[buf][1];
 		P.blobPitch = (uint32_t)(FG_CHUNK * FG_SLOT);
-		P.file2Off = (uint32_t)(h->d_slots[1] ? h->d_slots[1] - h->d_slots[0] : 0);
+		P.file2Off = (uint32_t)(h->d_slots[buf][1] ? h->d_slots[buf][1] - h->d_slots[buf][0] : 0);
 		cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 		if (h->timeKernels) {
 			while ((int)h->kev.size() < h->kevUsed + 3) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }
@@ -279,12 +310,30 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			h->kevUsed += 3;
 		}
 		if (!h->gzip) {
-			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, e2, true));
+			if (h->pending.valid) {
+				// this launch carries pass 2b of the previous batch
+				const ssc::GenParams& Q = h->pending.P;
+				P.nTilesPrev = Q.nTiles; P.nLoop = std::max(nTiles, Q.nTiles);
+				P.prevBlobs = Q.out1; P.prevFile2Off = Q.file2Off; P.prevBlobPitch = Q.blobPitch;
+				P.prevTileState = Q.tileState; P.prevPrefix = Q.blobPrefix;
+				P.prevDense1 = Q.dense1; P.prevDense2 = Q.dense2; P.prevCap1 = Q.cap1; P.prevCap2 = Q.cap2;
+				h->pending.valid = false;
+			}
+			grid = std::min((P.nLoop + FG_GEN - 1) / FG_GEN, h->smCount);
+			if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
+			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, s, e0, e1));
+			CK(ssc::launch_scan_blobs(P, s));
+			if (e2) CK(cudaEventRecord(e2, s));
+			h->pending.P = P; h->pending.valid = true;
 			h->stats.launches += 2;
 		} else {
 			// gzip mode: blobs -> (first batch of a plan: fit the Huffman table to a sample) -> one gzip member per blob -> pass 2 on the members
-			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, h->smCount, s, e0, e1, nullptr, false));
-			if (!h->haveGz) { int rc = build_gz_tables(h, P, nTiles); if (rc) return rc; }
+			int rc = flush_pending(h);
+			if (rc) return rc;
+			grid = std::min((nTiles + FG_GEN - 1) / FG_GEN, h->smCount);
+			if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
+			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, s, e0, e1));
+			if (!h->haveGz) { rc = build_gz_tables(h, P, nTiles); if (rc) return rc; }
 			CK(cudaMemsetAsync(h->d_gzLens.p, 0, sizeof(unsigned long long) * nTiles, s));
 			CK(ssc::launch_deflate_blobs(P.out1, P.out2, P.tileState, nTiles, P.blobPitch, h->d_gzBlobs[0], h->d_gzBlobs[1], h->d_gzLens.p,
 			                             FG_CHUNK * FG_SLOT, h->d_gzTab, &P.result->errorFlags, h->smCount, s));
@@ -292,18 +341,29 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			P2.out1 = h->d_gzBlobs[0]; P2.out2 = h->d_gzBlobs[1]; P2.tileState = h->d_gzLens.p; P2.blobPitch = FG_CHUNK * FG_SLOT;
 			CK(ssc::launch_pass2(P2, h->smCount, s));
 			if (e2) CK(cudaEventRecord(e2, s));
-			h->stats.launches += 3;
+			h->stats.launches += 4;
 		}
 	} else {
 		if (h->gzip) return fail(SSC_ERR_INVALID, "gzip output needs the fast kernel (kmer 3, read length 33..160)");
+		int rc = flush_pending(h);
+		if (rc) return rc;
 		ssc::GenVariant v = ssc::choose_variant(h->dt, h->fp64, h->smemLimit);
 		if (!v.ok) return fail(SSC_ERR_INVALID, "no kernel variant for read length %d / kmer %d", h->dt.RL, h->dt.K);
 		CK(ssc::launch_generate(P, v, grid, s));
+		h->stats.launches += 1;
 	}
 	CK(cudaMemcpyAsync(h->h_result[buf], h->d_result[buf], sizeof(ssc::BatchResult), cudaMemcpyDeviceToHost, s));
-	h->stats.launches += 2;
 	h->stats.gen_launches += 1;
 	return SSC_OK;
+}
+
+// error exit of a pipelined call: nothing of it may still be running when the caller sees the code
+int bail(ssc_handle* h, int rc) {
+	const std::string msg = g_err;
+	cudaDeviceSynchronize();
+	h->pending.valid = false;
+	g_err = msg;
+	return rc;
 }
 
 int check_result(ssc_handle* h, const ssc::BatchResult& r) {
@@ -344,6 +404,7 @@ static int init_handle(ssc_handle* h, int device) {
 		CK(cudaEventCreateWithFlags(&h->evCopy[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evCopy2[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evStage[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evDense[i], cudaEventDisableTiming));
 		CK(cudaMalloc((void**)&h->d_result[i], sizeof(ssc::BatchResult)));
 		CK(cudaMallocHost((void**)&h->h_result[i], sizeof(ssc::BatchResult)));
 	}
@@ -392,8 +453,8 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_isizeSym.release(); h->d_insSym.release(); h->d_delSym.release(); h->d_qualSym.release();
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
-	h->d_hap2.release(); h->d_hapN.release(); h->d_ref.release();
-	h->d_ticket2.release(); h->d_blobPrefix.release(); h->d_gzLens.release();
+	h->d_hap2.release(); h->d_hapN.release(); h->d_ref.release(); h->d_raw.release(); h->d_other.release();
+	h->d_ticket2.release(); h->d_gzLens.release();
 	for (int f = 0; f < 2; f++) if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]);
 	if (h->d_gzTab) cudaFree(h->d_gzTab);
 	h->d_cenStarts.release(); h->d_cenLens.release(); h->d_cenGc.release(); h->d_cenNn.release();
@@ -544,6 +605,52 @@ int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n) {
 	CK(cudaStreamSynchronize(h->compute));          // the caller may free the chromosome string
 	h->refSize = n;
 	h->stats.h2d_bytes += n;
+	return SSC_OK;
+}
+
+int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
+                               uint32_t line_bases, uint32_t line_width, uint64_t* n_other) {
+	if (!h || fd < 0) return fail(SSC_ERR_INVALID, "bad argument");
+	if (n_bases >= (1ull << 32) - 64 || (n_bases && (line_bases == 0 || line_width < line_bases)))
+		return fail(SSC_ERR_INVALID, "FASTA record geometry not supported (%llu bases, %u per line of %u bytes)",
+		            (unsigned long long)n_bases, line_bases, line_width);
+	CK(cudaSetDevice(h->device));
+	if (h->d_ref.n < n_bases + 16) CK(h->d_ref.alloc((size_t)n_bases + (size_t)n_bases / 8 + 4096));
+	if (h->d_raw.n < raw_len) CK(h->d_raw.alloc((size_t)raw_len + (size_t)raw_len / 8 + 4096));
+	if (!h->d_other.p) CK(h->d_other.alloc(1));
+	for (int i = 0; i < 2; i++) {
+		if (!h->h_stage[i]) CK(cudaMallocHost((void**)&h->h_stage[i], h->stageBytes));
+	}
+	cudaStream_t s = h->compute;
+	CK(cudaMemsetAsync(h->d_other.p, 0, 8, s));
+	// file -> pinned staging (pread) -> device, two staging buffers in turn: the read of chunk k+1 runs under the DMA of chunk k
+	// (and under the pack kernels of the previous chromosome that are still queued on the stream)
+	uint64_t done = 0;
+	int k = 0;
+	while (done < raw_len) {
+		const size_t chunk = (size_t)std::min<uint64_t>(h->stageBytes, raw_len - done);
+		CK(cudaEventSynchronize(h->evStage[k]));           // staging buffer k free again
+		size_t got = 0;
+		while (got < chunk) {
+			const ssize_t r = pread(fd, h->h_stage[k] + got, chunk - got, (off_t)(file_offset + done + got));
+			if (r < 0) { if (errno == EINTR) continue; return fail(SSC_ERR_INVALID, "reading the FASTA file failed: %s", strerror(errno)); }
+			if (r == 0) break;                             // a last line without a line feed ends the file early
+			got += (size_t)r;
+		}
+		if (got < chunk) memset(h->h_stage[k] + got, '\n', chunk - got);
+		CK(cudaMemcpyAsync(h->d_raw.p + done, h->h_stage[k], chunk, cudaMemcpyHostToDevice, s));
+		CK(cudaEventRecord(h->evStage[k], s));
+		h->stats.h2d_bytes += chunk;
+		done += chunk;
+		k ^= 1;
+	}
+	CK(ssc::launch_unfold(h->d_raw.p, raw_len, n_bases, line_bases, line_width, h->d_ref.p, h->d_other.p, s));
+	unsigned long long other = 0;
+	CK(cudaMemcpyAsync(&other, h->d_other.p, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	h->refSize = n_bases;
+	h->stats.launches += 1;
+	if (n_other) *n_other = other;
 	return SSC_OK;
 }
 
@@ -744,6 +851,7 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	for (size_t k = 1; k < devEmitBase.size(); k++)
 		if (devEmitBase[k] <= devEmitBase[k - 1]) return fail(SSC_ERR_INVALID, "segments must list their bins in increasing, non-overlapping order");
 	devEmitBase.push_back(h->emittedPairs);
+	h->devEmitBase = devEmitBase;
 	h->nDevBins = (int64_t)dev.size();
 	CK(h->d_bins.upload(dev, s));
 	CK(h->d_emitBase.upload(devEmitBase, s));
@@ -774,40 +882,48 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 	std::vector<Batch> batches;
 	for (int64_t e = eLo; e < eHi; e += h->slabPairs) batches.push_back({e, std::min(eHi, e + h->slabPairs)});
 	const int nb = (int)batches.size();
-	// pipeline: kernel(k+1) overlaps the device->host copy of batch k, which overlaps the sink of batch k-1
-	rc = launch_batch(h, 0, batches[0].lo, batches[0].hi);
-	if (rc) return rc;
-	CK(cudaEventRecord(h->evGen[0], h->compute));
+	// pipeline: the launch of batch k+1 (which also completes the dense slab of batch k) runs under the device->host copies of
+	// batch k (file 1 / file 2 on two streams), which run under the sink of batch k-1.  Slab hazards: the launch of batch k+1
+	// writes d_out[k & 1] (fused pass 2 of batch k) or d_out[(k+1) & 1] (other modes): the compute stream waits for every
+	// copy issued so far before it; h_out[k & 1] was consumed by the sink of batch k-2 an iteration ago.
+	auto launch = [&](int k) -> int {
+		for (int b = 0; b < 2; b++) {
+			CK(cudaStreamWaitEvent(h->compute, h->evCopy[b], 0));
+			CK(cudaStreamWaitEvent(h->compute, h->evCopy2[b], 0));
+		}
+		int r = launch_batch(h, k & 1, batches[k].lo, batches[k].hi);
+		if (r) return r;
+		CK(cudaEventRecord(h->evGen[k & 1], h->compute));
+		return SSC_OK;
+	};
+	rc = launch(0);
+	if (rc) return bail(h, rc);
 	ssc::BatchResult res[2];
 	for (int k = 0; k < nb; k++) {
 		const int buf = k & 1;
+		rc = k + 1 < nb ? launch(k + 1) : flush_pending(h);         // after this the dense slab of batch k is in the stream
+		if (rc) return bail(h, rc);
+		CK(cudaEventRecord(h->evDense[buf], h->compute));
 		CK(cudaEventSynchronize(h->evGen[buf]));
 		res[buf] = *h->h_result[buf];
 		rc = check_result(h, res[buf]);
-		if (rc) { cudaDeviceSynchronize(); return rc; }
+		if (rc) return bail(h, rc);
+		CK(cudaStreamWaitEvent(h->copy, h->evDense[buf], 0));
 		CK(cudaMemcpyAsync(h->h_out[buf][0], h->d_out[buf][0], res[buf].bytes1, cudaMemcpyDeviceToHost, h->copy));
-		if (nFiles == 2) CK(cudaMemcpyAsync(h->h_out[buf][1], h->d_out[buf][1], res[buf].bytes2, cudaMemcpyDeviceToHost, h->copy2));
 		CK(cudaEventRecord(h->evCopy[buf], h->copy));
+		if (nFiles == 2) {
+			CK(cudaStreamWaitEvent(h->copy2, h->evDense[buf], 0));
+			CK(cudaMemcpyAsync(h->h_out[buf][1], h->d_out[buf][1], res[buf].bytes2, cudaMemcpyDeviceToHost, h->copy2));
+		}
 		CK(cudaEventRecord(h->evCopy2[buf], h->copy2));
 		h->stats.d2h_bytes += res[buf].bytes1 + res[buf].bytes2;
 		if (k >= 1) {
-			// sink batch k-1 (its copy was issued in the previous iteration)
 			const int pb = (k - 1) & 1;
 			CK(cudaEventSynchronize(h->evCopy[pb]));
 			CK(cudaEventSynchronize(h->evCopy2[pb]));
-			if (k + 1 < nb) {
-				// device slab pb is free again: launch batch k+1 into it before the host-side sink work
-				rc = launch_batch(h, pb, batches[k + 1].lo, batches[k + 1].hi);
-				if (rc) return rc;
-				CK(cudaEventRecord(h->evGen[pb], h->compute));
-			}
 			int src = sink(user, (const char*)h->h_out[pb][0], res[pb].bytes1, nFiles == 2 ? (const char*)h->h_out[pb][1] : nullptr,
 			               nFiles == 2 ? res[pb].bytes2 : 0, batches[k - 1].lo, batches[k - 1].hi - batches[k - 1].lo);
-			if (src) { cudaDeviceSynchronize(); return fail(SSC_ERR_SINK, "sink returned %d", src); }
-		} else if (nb > 1) {
-			rc = launch_batch(h, 1, batches[1].lo, batches[1].hi);
-			if (rc) return rc;
-			CK(cudaEventRecord(h->evGen[1], h->compute));
+			if (src) { fail(SSC_ERR_SINK, "sink returned %d", src); return bail(h, SSC_ERR_SINK); }
 		}
 	}
 	{
@@ -842,13 +958,20 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_
 				CK(cudaEventSynchronize(h->evGen[buf]));
 				ssc::BatchResult r = *h->h_result[buf];
 				rc = check_result(h, r);
-				if (rc) { cudaDeviceSynchronize(); return rc; }
+				if (rc) return bail(h, rc);
 				b1 += r.bytes1; b2 += r.bytes2; nb += r.bases;
 			}
 			rc = launch_batch(h, buf, e, std::min(eHi, e + h->slabPairs));
-			if (rc) return rc;
+			if (rc) return bail(h, rc);
 			CK(cudaEventRecord(h->evGen[buf], h->compute));
 		}
+		// the last batch's blobs: stand-alone move, timed with the scans as "pass 2"
+		while ((int)h->kev.size() < h->kevUsed + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->kev.push_back(e); }
+		const int fl = h->kevUsed;
+		CK(cudaEventRecord(h->kev[fl], h->compute));
+		rc = flush_pending(h);
+		if (rc) return bail(h, rc);
+		CK(cudaEventRecord(h->kev[fl + 1], h->compute));
 		CK(cudaEventRecord(h->evStop, h->compute));
 		CK(cudaEventSynchronize(h->evStop));
 		for (int j = std::max(0, k - 2); j < k; j++) {
@@ -865,6 +988,11 @@ int ssc_generate_device(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, uint64_
 			CK(cudaEventElapsedTime(&a, h->kev[i], h->kev[i + 1]));
 			CK(cudaEventElapsedTime(&b, h->kev[i + 1], h->kev[i + 2]));
 			h->stats.gen_kernel_ms += a; h->stats.compact_kernel_ms += b; h->stats.timed_batches += 1;
+		}
+		{
+			float c = 0;
+			CK(cudaEventElapsedTime(&c, h->kev[fl], h->kev[fl + 1]));
+			h->stats.compact_kernel_ms += c;
 		}
 	}
 	if (bytes1) *bytes1 = b1;

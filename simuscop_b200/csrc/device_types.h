@@ -85,6 +85,14 @@ struct GenParams {
 	uint8_t* dense1; uint8_t* dense2;   // fast kernel: final slabs (pass 2)
 	unsigned long long cap1, cap2;
 	BatchResult* result;
+	// fast kernel, pass 2 folded into the next launch: while a warp generates ticket j of this batch it also moves blob j of
+	// the PREVIOUS batch (lengths and offsets final since that batch's scan) to its place in that batch's dense slab.
+	// nTilesPrev == 0: nothing to move; nLoop = max(nTiles, nTilesPrev) tickets are handed out.
+	int nTilesPrev, nLoop;
+	const uint8_t* prevBlobs; uint32_t prevFile2Off; uint32_t prevBlobPitch;
+	const unsigned long long* prevTileState; const unsigned long long* prevPrefix;
+	uint8_t* prevDense1; uint8_t* prevDense2;
+	unsigned long long prevCap1, prevCap2;
 };
 
 }  // namespace ssc

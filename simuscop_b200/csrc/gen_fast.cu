@@ -574,20 +574,27 @@ __global__ void __launch_bounds__(SC_THREADS) scan_blobs_kernel(const GenParams 
 	}
 }
 
-// pass 2b: one warp per blob
+// pass 2b: blob j of a batch -> its place in the dense slabs (one warp)
+__device__ __forceinline__ void move_blob(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
+                                          const unsigned long long* __restrict__ tileState, const unsigned long long* __restrict__ prefix,
+                                          uint8_t* __restrict__ dense1, uint8_t* __restrict__ dense2, unsigned long long cap1,
+                                          unsigned long long cap2, int j, int lane) {
+	const unsigned long long excl = __ldcg(prefix + j), mine = __ldcg(tileState + j);
+	const unsigned long long d1 = excl >> 31, d2 = excl & 0x7fffffffull;
+	const int l1 = (int)(mine >> 31), l2 = (int)(mine & 0x7fffffffull);
+	if (d1 + (unsigned)l1 > cap1 || d2 + (unsigned)l2 > cap2) return;   // flagged by the scan
+	const size_t blob = (size_t)j * blobPitch;
+	copy_realign(blobs1 + blob, l1, dense1 + d1, lane);
+	if (l2) copy_realign(blobs2 + blob, l2, dense2 + d2, lane);
+}
+
+// stand-alone form: the last batch of a call (nothing follows that could carry its moves) and the gzip members
 static constexpr int CP_THREADS = 256;
 __global__ void __launch_bounds__(CP_THREADS, 8) move_blobs_kernel(const GenParams P) {
 	const int lane = threadIdx.x & 31;
 	const int nWarps = gridDim.x * (CP_THREADS / 32);
-	for (int j = blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5); j < P.nTiles; j += nWarps) {
-		const unsigned long long excl = P.blobPrefix[j], mine = P.tileState[j];
-		const unsigned long long d1 = excl >> 31, d2 = excl & 0x7fffffffull;
-		const int l1 = (int)(mine >> 31), l2 = (int)(mine & 0x7fffffffull);
-		if (d1 + (unsigned)l1 > P.cap1 || d2 + (unsigned)l2 > P.cap2) continue;   // flagged by the scan
-		const size_t blob = (size_t)j * P.blobPitch;
-		copy_realign(P.out1 + blob, l1, P.dense1 + d1, lane);
-		if (l2) copy_realign(P.out2 + blob, l2, P.dense2 + d2, lane);
-	}
+	for (int j = blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5); j < P.nTiles; j += nWarps)
+		move_blob(P.out1, P.out2, P.blobPitch, P.tileState, P.blobPrefix, P.dense1, P.dense2, P.cap1, P.cap2, j, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -728,7 +735,8 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		int chunk = 0;
 		if (lane == 0) chunk = (int)atomicAdd(P.ticket2, 1u);
 		chunk = __shfl_sync(0xffffffffu, chunk, 0);
-		if (chunk >= P.nTiles) break;
+		if (chunk >= P.nLoop) break;
+		if (chunk < P.nTiles) {
 		// slot = pair index inside the batch (a batch has < 2^31 / FG_SLOT pairs)
 		const uint32_t slot0 = (uint32_t)chunk * FG_CHUNK;
 		const uint32_t nSlots = (uint32_t)(P.emitHi - P.emitLo);
@@ -967,6 +975,13 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				atomicAdd(&P.result->rawBytes, (unsigned long long)len1 + len2);
 			}
 		}
+		}
+		// ---- pass 2 of the previous batch, carried by this launch: blob `chunk` of that batch to its dense place.  The blob
+		// lies in HBM since the previous launch and its offset is final, so nothing is waited for; the loads are in flight
+		// while the other warps of the SM keep generating.
+		if (chunk < P.nTilesPrev)
+			move_blob(P.prevBlobs, P.prevBlobs + P.prevFile2Off, P.prevBlobPitch, P.prevTileState, P.prevPrefix, P.prevDense1, P.prevDense2,
+			          P.prevCap1, P.prevCap2, chunk, lane);
 	}
 
 }
@@ -1026,9 +1041,10 @@ static cudaError_t launch_fast_variant(const GenParams& P, size_t smemBytes, int
 	return cudaGetLastError();
 }
 
-// P.out1/out2 = blob scratch, P.dense1/dense2 = final slabs, P.nTiles = tickets of FG_CHUNK pairs
-cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
-                                 cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool pass2) {
+// P.out1/out2 = blob scratch, P.dense1/dense2 = final slabs, P.nTiles = tickets of FG_CHUNK pairs.  Launches pass 1 (which
+// also carries the moves of the previous batch when P.nTilesPrev > 0); events e0/e1 (optional) bracket the kernel.
+cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, cudaStream_t stream,
+                                 cudaEvent_t e0, cudaEvent_t e1) {
 	const int nch = (P.t.RL + 31) / 32;   // the kernel's chunk count is exact: only the last chunk has idle lanes
 	cudaError_t e;
 	if (e0) cudaEventRecord(e0, stream);
@@ -1050,19 +1066,29 @@ cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes
 	}
 	if (e != cudaSuccess) return e;
 	if (e1) cudaEventRecord(e1, stream);
-	if (!pass2) return cudaSuccess;
-	e = launch_pass2(P, smCount, stream);
-	if (e2) cudaEventRecord(e2, stream);
-	return e;
+	return cudaSuccess;
+}
+
+// pass 2a alone: blob lengths P.tileState -> offsets P.blobPrefix, totals in P.result->bytes1/2
+cudaError_t launch_scan_blobs(const GenParams& P, cudaStream_t stream) {
+	scan_blobs_kernel<<<1, SC_THREADS, 0, stream>>>(P);
+	return cudaGetLastError();
+}
+
+// pass 2b alone: blobs P.out1/out2 -> dense slabs P.dense1/dense2 at the offsets of the scan
+cudaError_t launch_move_blobs(const GenParams& P, int smCount, cudaStream_t stream) {
+	int cgrid = smCount * 8;
+	if (cgrid * (CP_THREADS / 32) > P.nTiles) cgrid = (P.nTiles + CP_THREADS / 32 - 1) / (CP_THREADS / 32);
+	if (cgrid < 1) cgrid = 1;
+	move_blobs_kernel<<<cgrid, CP_THREADS, 0, stream>>>(P);
+	return cudaGetLastError();
 }
 
 // pass 2: blobs P.out1/out2 with packed lengths P.tileState -> dense slabs P.dense1/dense2, totals in P.result->bytes1/2
 cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream) {
-	scan_blobs_kernel<<<1, SC_THREADS, 0, stream>>>(P);
-	int cgrid = smCount * 8;
-	if (cgrid * (CP_THREADS / 32) > P.nTiles) cgrid = (P.nTiles + CP_THREADS / 32 - 1) / (CP_THREADS / 32);
-	move_blobs_kernel<<<cgrid, CP_THREADS, 0, stream>>>(P);
-	return cudaGetLastError();
+	cudaError_t e = launch_scan_blobs(P, stream);
+	if (e != cudaSuccess) return e;
+	return launch_move_blobs(P, smCount, stream);
 }
 
 }  // namespace ssc

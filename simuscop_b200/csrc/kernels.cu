@@ -738,6 +738,46 @@ cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, c
 	return launch_variant<10, false, false, false>(P, grid, v.smemBytes, stream);
 }
 
+// ----------------------------------------------------------------------------------------
+// unfold_kernel: the sequence lines of one FASTA record as they lie in the file (raw, line feeds included) -> the
+// chromosome string the reference works on: line ends dropped, upper case (FastaReference::getSequence,
+// lib/fastahack/Fasta.cpp:304-334, then Genome::getSubSequence's toupper).  The .fai entry gives the geometry: every
+// line but the last holds lineBases bases in lineWidth bytes, so base i sits at raw[i + (i / lineBases) * (lineWidth -
+// lineBases)].  One thread per 16 bases; *other counts the characters that are neither ACGT nor N (IUPAC codes: the host
+// keeps such chromosomes on its own string path, see host_plan.cpp).
+// ----------------------------------------------------------------------------------------
+__global__ void unfold_kernel(const uint8_t* __restrict__ raw, uint64_t rawLen, uint32_t nBases, uint32_t lineBases, uint32_t pad,
+                              uint8_t* __restrict__ out, unsigned long long* __restrict__ other) {
+	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+	uint32_t bad = 0;
+	if (i0 < nBases) {
+		uint32_t line = i0 / lineBases, col = i0 - line * lineBases;
+		uint64_t src = (uint64_t)i0 + (uint64_t)line * pad;
+		uint32_t w[4] = {0u, 0u, 0u, 0u};
+		const uint32_t n = min(16u, nBases - i0);
+		for (uint32_t k = 0; k < n; k++) {
+			uint32_t c = src < rawLen ? raw[src] : (uint32_t)'N';
+			if (c - 'a' < 26u) c -= 32u;
+			bad += !(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N');
+			w[k >> 2] |= c << (8 * (k & 3));
+			src++;
+			if (++col == lineBases) { col = 0; src += pad; }
+		}
+		if (n == 16u) *(uint4*)(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+		else for (uint32_t k = 0; k < n; k++) out[i0 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+	}
+	bad = __reduce_add_sync(0xffffffffu, bad);
+	if (bad && (threadIdx.x & 31) == 0) atomicAdd(other, (unsigned long long)bad);
+}
+
+cudaError_t launch_unfold(const uint8_t* raw, uint64_t rawLen, uint64_t nBases, uint32_t lineBases, uint32_t lineWidth, uint8_t* out,
+                          unsigned long long* other, cudaStream_t stream) {
+	if (nBases == 0) return cudaSuccess;
+	const uint64_t threads = (nBases + 15) / 16;
+	unfold_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(raw, rawLen, (uint32_t)nBases, lineBases, lineWidth - lineBases, out, other);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, uint32_t* hap2, uint32_t* hapN,
                         const int8_t* lut, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;

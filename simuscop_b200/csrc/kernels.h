@@ -36,13 +36,17 @@ GenVariant choose_variant(const DevTables& t, bool fp64, int smemLimit);
 cudaError_t launch_generate(const GenParams& P, const GenVariant& v, int grid, cudaStream_t stream);
 bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemBytes);   // qmode: 8 / 2 / 0, see gen_fast.cu
 int fast_choose_qbins(int B, int RL);
-cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, int smCount, cudaStream_t stream,
-                                 cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool pass2);
+cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes, int grid, cudaStream_t stream,
+                                 cudaEvent_t e0, cudaEvent_t e1);
+cudaError_t launch_scan_blobs(const GenParams& P, cudaStream_t stream);
+cudaError_t launch_move_blobs(const GenParams& P, int smCount, cudaStream_t stream);
 cudaError_t launch_issue_floor(int mode, int RL, int64_t nPairs, uint64_t seed, int grid, uint32_t* scratch, uint8_t* blobs,
                                uint32_t blobPitch, uint32_t file2Off, cudaStream_t stream);   // floor.cu
 cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t* ascii, uint64_t n, uint64_t firstBase, uint32_t* hap2, uint32_t* hapN,
                         const int8_t* lut, cudaStream_t stream);
+cudaError_t launch_unfold(const uint8_t* raw, uint64_t rawLen, uint64_t nBases, uint32_t lineBases, uint32_t lineWidth, uint8_t* out,
+                          unsigned long long* other, cudaStream_t stream);
 cudaError_t launch_census(const DevTables& t, bool fp64, const CensusBin* bins, int nBins, uint64_t seed,
                           uint16_t* riskyAttempt, int32_t* emitted, cudaStream_t stream);
 cudaError_t launch_poke(uint32_t* hap2, uint32_t* hapN, const int64_t* pos, const uint8_t* chars, int64_t n, const int8_t* lut, cudaStream_t stream);

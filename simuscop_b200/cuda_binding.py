@@ -11,7 +11,7 @@ from . import abi
 from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
-           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
+           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_reference_upload_fasta", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
            "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host", "ssc_issue_floor"]
 
 _lib = None
@@ -34,6 +34,8 @@ def lib():
         L.ssc_genome_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ssc_genome_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ssc_reference_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        L.ssc_reference_upload_fasta.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                 C.POINTER(C.c_uint64)]
         L.ssc_genome_append_ref.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
         L.ssc_genome_poke.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
         L.ssc_genome_read.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -123,8 +125,9 @@ class Generator:
         self.planned, self.emitted = pp.value, ep.value
         return self.planned, self.emitted
 
-    def generate(self, lo=0, hi=None, sink=None):
-        """Stream pairs [lo, hi) through the pinned host slabs. Without `sink` returns (fq1, fq2) bytes."""
+    def generate(self, lo=0, hi=None, sink=None, user=None):
+        """Stream pairs [lo, hi) through the pinned host slabs. Without `sink` returns (fq1, fq2) bytes.  `sink`: a Python
+        callable or a C function (an abi.SINK_FN instance, e.g. the file writer of libsimuscop_host) called with `user`."""
         if hi is None:
             hi = self.planned
         parts1, parts2 = [], []
@@ -134,8 +137,8 @@ class Generator:
             if b2:
                 parts2.append(C.string_at(b2, l2))
             return 0
-        cb = abi.SINK_FN(sink if sink is not None else collect)
-        _ck(lib().ssc_generate(self.h, lo, hi, cb, None))
+        cb = sink if isinstance(sink, abi.SINK_FN) else abi.SINK_FN(sink if sink is not None else collect)
+        _ck(lib().ssc_generate(self.h, lo, hi, cb, user))
         if sink is None:
             return b"".join(parts1), b"".join(parts2)
 

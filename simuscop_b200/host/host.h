@@ -44,7 +44,11 @@ public:
 	// positions of the cached chromosome that hold neither ACGT nor N (IUPAC codes): calculateGCPercent
 	// (lib/mydefine/MyDefine.cpp:279-303) counts only a literal 'N' as unknown, the device mask every non-ACGT character
 	bool other_in(size_t a, size_t b) const;
+	const FastaEntry* entry(const std::string& chr) const;   // .fai geometry of a record, nullptr when unknown
+	int fd();                                                // the FASTA file, opened read-only on first use
+	~Fasta();
 private:
+	int fd_ = -1;
 	std::vector<size_t> cachedOther_;
 	std::string path_;
 	std::map<std::string, FastaEntry> idx_;

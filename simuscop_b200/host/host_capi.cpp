@@ -8,6 +8,9 @@
 #include <algorithm>
 #include <iostream>
 #include <string>
+#include <cerrno>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -18,27 +21,100 @@ struct ssh_job {
 	sschost::Job job;
 };
 
-namespace {
-struct FileSink {
-	int fd1 = -1, fd2 = -1;
+// ------------------------------------------------------------------------------------------------
+// Output side: SeqWriter's role (lib/seqwriter/SeqWriter.cpp:41-54: append the slab(s) to the FASTQ file(s), both files
+// advancing together) at the rate a GPU produces slabs.  A slab of ~0.7 GB per file is cut into chunks that a small pool of
+// threads pwrite()s at their final offsets in parallel (page-cache / tmpfs copies scale with threads; a real device sees a
+// deeper queue); the call returns when the slab is on its way to the file, because the pinned slab is reused afterwards.
+// ------------------------------------------------------------------------------------------------
+struct ssh_writer {
+	int fd[2] = {-1, -1};
+	uint64_t off[2] = {0, 0};
+	int nThreads = 1;
+	std::vector<std::thread> pool;
+	std::mutex mu;
+	std::condition_variable cvWork, cvDone;
+	struct Chunk { int fd; const char* p; size_t n; uint64_t off; };
+	std::vector<Chunk> queue;
+	size_t next = 0, inFlight = 0;
+	bool stop = false;
+	int err = 0;
+	// turnstile for several producers (one per GPU) that deliver batches out of order: batch k is written when every
+	// batch before it has been
+	int64_t turn = 0;
+	std::condition_variable cvTurn;
+
+	static int pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
+		while (n > 0) {
+			ssize_t w = pwrite(fd, p, n, (off_t)off);
+			if (w < 0) { if (errno == EINTR) continue; return errno ? errno : EIO; }
+			p += w; n -= (size_t)w; off += (uint64_t)w;
+		}
+		return 0;
+	}
+	void worker() {
+		std::unique_lock<std::mutex> lk(mu);
+		while (true) {
+			cvWork.wait(lk, [&] { return stop || next < queue.size(); });
+			if (stop && next >= queue.size()) return;
+			const Chunk c = queue[next++];
+			inFlight++;
+			lk.unlock();
+			const int e = pwrite_all(c.fd, c.p, c.n, c.off);
+			lk.lock();
+			if (e && !err) err = e;
+			inFlight--;
+			if (next >= queue.size() && inFlight == 0) cvDone.notify_all();
+		}
+	}
+	// both slabs to their files at the running offsets; returns when written
+	int write_slabs(const char* b1, size_t l1, const char* b2, size_t l2) {
+		static const size_t CH = 8u << 20;
+		std::unique_lock<std::mutex> lk(mu);
+		queue.clear(); next = 0;
+		const char* bufs[2] = {b1, b2}; const size_t lens[2] = {l1, fd[1] >= 0 ? l2 : 0};
+		for (int f = 0; f < 2; f++) {
+			for (size_t o = 0; o < lens[f]; o += CH) queue.push_back(Chunk{fd[f], bufs[f] + o, std::min(CH, lens[f] - o), off[f] + o});
+			off[f] += lens[f];
+		}
+		if (queue.empty()) return 0;
+		if (pool.empty()) {           // single-threaded: write here
+			for (const Chunk& c : queue) { const int e = pwrite_all(c.fd, c.p, c.n, c.off); if (e && !err) err = e; }
+			queue.clear();
+			return err;
+		}
+		cvWork.notify_all();
+		cvDone.wait(lk, [&] { return next >= queue.size() && inFlight == 0; });
+		return err;
+	}
 };
 
-int write_all(int fd, const char* p, size_t n) {
-	while (n > 0) {
-		ssize_t w = write(fd, p, n);
-		if (w < 0) return 1;
-		p += w; n -= (size_t)w;
-	}
-	return 0;
+namespace {
+
+// sink of a single producer: batches arrive in order
+int writer_sink(void* user, const char* b1, size_t l1, const char* b2, size_t l2, int64_t, int64_t) {
+	return ((ssh_writer*)user)->write_slabs(b1, l1, b2, l2) ? 1 : 0;
 }
 
-// SeqWriter::write(char*, char*), lib/seqwriter/SeqWriter.cpp:49-54: both files advance together
-int file_sink(void* user, const char* b1, size_t l1, const char* b2, size_t l2, int64_t, int64_t) {
-	FileSink* s = (FileSink*)user;
-	if (write_all(s->fd1, b1, l1)) return 1;
-	if (s->fd2 >= 0 && write_all(s->fd2, b2, l2)) return 1;
-	return 0;
+// sink of one of several producers: `batch` is the global index of the (single) batch this ssc_generate call covers
+struct TurnSink { ssh_writer* w; int64_t batch; };
+int turn_sink(void* user, const char* b1, size_t l1, const char* b2, size_t l2, int64_t, int64_t) {
+	TurnSink* t = (TurnSink*)user;
+	ssh_writer* w = t->w;
+	{
+		std::unique_lock<std::mutex> lk(w->mu);
+		w->cvTurn.wait(lk, [&] { return w->turn == t->batch || w->err; });
+		if (w->err) return 1;
+	}
+	const int e = w->write_slabs(b1, l1, b2, l2);
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		w->turn = t->batch + 1;
+	}
+	w->cvTurn.notify_all();
+	return e ? 1 : 0;
 }
+
 }  // namespace
 
 extern "C" {
@@ -62,6 +138,41 @@ const char* ssh_output_dir(ssh_job* job) { return job->job.cfg.str["output"].c_s
 int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_path, int64_t* planned, int64_t* emitted) {
 	if (!job || s < 0 || s >= (int)job->job.samples.size()) return SSC_ERR_INVALID;
 	return job->job.prepare_sample(s, dev, dump_path ? dump_path : "", planned, emitted);
+}
+
+int ssh_writer_open(const char* path1, const char* path2, int threads, ssh_writer** out) {
+	if (!path1 || !out) return SSC_ERR_INVALID;
+	ssh_writer* w = new ssh_writer();
+	w->fd[0] = open(path1, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+	if (path2 && path2[0]) w->fd[1] = open(path2, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+	if (w->fd[0] < 0 || (path2 && path2[0] && w->fd[1] < 0)) {
+		if (w->fd[0] >= 0) close(w->fd[0]);
+		if (w->fd[1] >= 0) close(w->fd[1]);
+		delete w;
+		return SSC_ERR_SINK;
+	}
+	w->nThreads = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+	if (w->nThreads > 1) for (int i = 0; i < w->nThreads; i++) w->pool.emplace_back([w] { w->worker(); });
+	*out = w;
+	return SSC_OK;
+}
+
+ssc_sink_fn ssh_writer_sink(void) { return writer_sink; }
+
+int ssh_writer_close(ssh_writer* w, uint64_t* bytes1, uint64_t* bytes2) {
+	if (!w) return SSC_OK;
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		w->stop = true;
+	}
+	w->cvWork.notify_all();
+	for (auto& t : w->pool) t.join();
+	int rc = w->err ? SSC_ERR_SINK : SSC_OK;
+	for (int f = 0; f < 2; f++) if (w->fd[f] >= 0 && close(w->fd[f]) != 0) rc = SSC_ERR_SINK;
+	if (bytes1) *bytes1 = w->off[0];
+	if (bytes2) *bytes2 = w->off[1];
+	delete w;
+	return rc;
 }
 
 int ssh_run(ssh_job* job, int device) {
@@ -109,47 +220,51 @@ int ssh_run(ssh_job* job, int device) {
 		int64_t planned = 0, emitted = 0;
 		rc = J.prepare_sample_multi(s, devs, dump, &planned, &emitted);
 		if (rc) { std::cerr << "Error: " << ssc_last_error() << std::endl; break; }
-		// shard g writes <file>.part<g> (g > 0) or the final file (g == 0); parts are appended in rank order afterwards
-		std::vector<FileSink> sinks(G);
-		std::vector<int> rcs(G, 0);
-		std::vector<std::string> errs(G);
-		auto part = [&](const std::string& f, int g) { return g == 0 ? f : f + ".part" + std::to_string(g); };
-		for (int g = 0; g < G; g++) {
-			sinks[g].fd1 = open(part(f1, g).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-			if (sinks[g].fd1 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + part(f1, g));
-			if (paired) {
-				sinks[g].fd2 = open(part(f2, g).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-				if (sinks[g].fd2 < 0) sschost::die(-1, "Error: can not open fastq file to save results:\n" + part(f2, g));
-			}
+		// one ordered writer per sample.  One GPU: a single ssc_generate call over the whole job (the library pipelines kernel,
+		// device->host copy and sink).  Several GPUs: the job is cut into batches, batch k goes to GPU k mod G, and every
+		// finished slab waits at the writer's turnstile until all earlier batches are in the file -- one pass of I/O, no part
+		// files, output identical to the single-GPU run.
+		ssh_writer* w = nullptr;
+		int wthreads = 4;
+		if (const char* wt = getenv("SIMUSCOP_WRITER_THREADS")) wthreads = atoi(wt);
+		if (ssh_writer_open(f1.c_str(), paired ? f2.c_str() : nullptr, wthreads, &w))
+			sschost::die(-1, "Error: can not open fastq file to save results:\n" + f1);
+		if (G == 1) {
+			rc = ssc_generate(devs[0], 0, planned, writer_sink, w);
+			if (rc) std::cerr << "Error: " << ssc_last_error() << std::endl;
+		} else {
+			int64_t bp = 1 << 20;
+			if (const char* bpe = getenv("SIMUSCOP_BATCH_PAIRS")) bp = std::max<int64_t>(32, atoll(bpe));
+			const int64_t nBatches = (planned + bp - 1) / bp;
+			std::vector<int> rcs(G, 0);
+			std::vector<std::string> errs(G);
+			auto work = [&](int g) {
+				for (int64_t k = g; k < nBatches; k += G) {
+					TurnSink ts{w, k};
+					// a batch without emitted pairs never reaches the sink: pass its turn on here
+					bool called = false;
+					struct Ctx { TurnSink* ts; bool* called; } ctx{&ts, &called};
+					auto thunk = [](void* u, const char* b1, size_t l1, const char* b2, size_t l2, int64_t a, int64_t n) -> int {
+						Ctx* c = (Ctx*)u; *c->called = true; return turn_sink(c->ts, b1, l1, b2, l2, a, n);
+					};
+					rcs[g] = ssc_generate(devs[g], k * bp, std::min(planned, (k + 1) * bp), thunk, &ctx);
+					if (rcs[g]) { errs[g] = ssc_last_error(); std::lock_guard<std::mutex> lk(w->mu); if (!w->err) w->err = EIO; w->cvTurn.notify_all(); return; }
+					if (!called) {
+						std::unique_lock<std::mutex> lk(w->mu);
+						w->cvTurn.wait(lk, [&] { return w->turn == k || w->err; });
+						w->turn = k + 1;
+						lk.unlock();
+						w->cvTurn.notify_all();
+					}
+				}
+			};
+			std::vector<std::thread> th;
+			for (int g = 1; g < G; g++) th.emplace_back(work, g);
+			work(0);
+			for (auto& t : th) t.join();
+			for (int g = 0; g < G; g++) if (rcs[g]) { std::cerr << "Error: " << errs[g] << std::endl; rc = rcs[g]; }
 		}
-		auto work = [&](int g) {
-			const int64_t base = planned / G, extra = planned % G;
-			const int64_t lo = g * base + std::min<int64_t>(g, extra), hi = lo + base + (g < extra ? 1 : 0);
-			rcs[g] = ssc_generate(devs[g], lo, hi, file_sink, &sinks[g]);
-			if (rcs[g]) errs[g] = ssc_last_error();
-		};
-		std::vector<std::thread> th;
-		for (int g = 1; g < G; g++) th.emplace_back(work, g);
-		work(0);
-		for (auto& t : th) t.join();
-		for (int g = 0; g < G; g++) if (rcs[g]) { std::cerr << "Error: " << errs[g] << std::endl; rc = rcs[g]; }
-		// ordered concatenation of the shards
-		for (int g = 1; g < G && !rc; g++) {
-			for (int f = 0; f < (paired ? 2 : 1); f++) {
-				const int src = f == 0 ? sinks[g].fd1 : sinks[g].fd2;
-				const int dst = f == 0 ? sinks[0].fd1 : sinks[0].fd2;
-				close(src);
-				const std::string pf = part(f == 0 ? f1 : f2, g);
-				int in = open(pf.c_str(), O_RDONLY);
-				std::vector<char> buf(8u << 20);
-				ssize_t n;
-				while (in >= 0 && (n = read(in, buf.data(), buf.size())) > 0) if (write_all(dst, buf.data(), (size_t)n)) { rc = SSC_ERR_SINK; break; }
-				if (in >= 0) close(in);
-				unlink(pf.c_str());
-			}
-		}
-		close(sinks[0].fd1);
-		if (sinks[0].fd2 >= 0) close(sinks[0].fd2);
+		if (ssh_writer_close(w, nullptr, nullptr) && !rc) { std::cerr << "Error: writing " << f1 << " failed" << std::endl; rc = SSC_ERR_SINK; }
 	}
 	for (auto* d : devs) ssc_destroy(d);
 	return rc;

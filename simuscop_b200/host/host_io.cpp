@@ -1,4 +1,5 @@
 // host_io.cpp -- configuration file, FASTA/.fai, SNP / variation / target / abundance loaders.
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -178,6 +179,18 @@ bool Fasta::other_in(size_t a, size_t b) const {
 	auto it = std::lower_bound(cachedOther_.begin(), cachedOther_.end(), a);
 	return it != cachedOther_.end() && *it < b;
 }
+
+const FastaEntry* Fasta::entry(const std::string& chr) const {
+	auto it = idx_.find(chr);
+	return it == idx_.end() ? nullptr : &it->second;
+}
+
+int Fasta::fd() {
+	if (fd_ < 0) fd_ = ::open(path_.c_str(), O_RDONLY);
+	return fd_;
+}
+
+Fasta::~Fasta() { if (fd_ >= 0) ::close(fd_); }
 
 long Fasta::length(const std::string& chr) const {
 	auto it = idx_.find(chr);

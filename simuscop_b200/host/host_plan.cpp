@@ -227,7 +227,7 @@ static inline bool is_acgtn(char ch) { const char c = (char)(ch & 0xDF); return 
 namespace {
 // phase timers of the plan construction (printed when SIMUSCOP_TIMING is set)
 struct PhaseTimers {
-	double build = 0, gc = 0, upload = 0, counts = 0, census = 0, enumerate = 0;
+	double build = 0, gc = 0, upload = 0, counts = 0, census = 0, enumerate = 0, flatten = 0, setPlan = 0;
 	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 } g_tm;
 }  // namespace
@@ -376,7 +376,28 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		double t0 = PhaseTimers::now();
 		// segments without indel variants are built on the device from the uploaded chromosome (copies + substitutions);
 		// the others as host strings (Segment::generateSegSequences' insert / erase arithmetic stays on the host)
-		const std::string& chrSeq = fasta.chromosome(chr);
+		// The chromosome goes to the device straight from the FASTA file (raw lines -> pinned staging -> unfold kernel); the
+		// host reads and upper-cases it only when it needs the string itself: a segment with insertion / deletion variants,
+		// or IUPAC codes in the record (the count comes back from the unfold kernel).
+		const FastaEntry* fe = fasta.entry(chr);
+		const size_t chrLen = fe ? (size_t)fe->length : 0;
+		bool needHost = !useRefBuild || !fe || fe->line_blen <= 0;
+		for (size_t k = 0; k < v.size() && !needHost; k++) if (!segment_is_copy_only(v[k], popu)) needHost = true;
+		bool devRef = false;
+		if (useRefBuild && fe && fe->line_blen > 0 && chrLen > 0) {
+			const uint64_t lines = (uint64_t)((chrLen - 1) / (size_t)fe->line_blen);          // full lines in front of the last one
+			const uint64_t rawLen = (uint64_t)chrLen + lines * (uint64_t)(fe->line_len - fe->line_blen);
+			uint64_t nOther = 0;
+			for (ssc_handle* dev : devs) {
+				rc = ssc_reference_upload_fasta(dev, fasta.fd(), (uint64_t)fe->offset, rawLen, (uint64_t)chrLen, (uint32_t)fe->line_blen,
+				                                (uint32_t)fe->line_len, &nOther);
+				if (rc) return rc;
+			}
+			devRef = true;
+			if (nOther > 0) needHost = true;
+		}
+		static const std::string noSeq;
+		const std::string& chrSeq = needHost ? fasta.chromosome(chr) : noSeq;
 		std::vector<std::vector<std::string>> haps(v.size());
 		std::vector<std::vector<int>> reps(v.size());
 		std::vector<std::vector<Poke>> pokes(v.size());
@@ -385,13 +406,13 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		bool anyDev = false;
 		for (size_t k = 0; k < v.size(); k++) {
 			const size_t refOff = (size_t)(v[k].start - 1);
-			const size_t refLen = std::min((size_t)v[k].refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
+			const size_t refLen = std::min((size_t)v[k].refSize(), chrLen > refOff ? chrLen - refOff : 0);
 			refOffs[k] = refOff; refLens[k] = refLen;
 			// The device census counts every non-ACGT character as unknown; the reference only a literal 'N'
 			// (calculateGCPercent, MyDefine.cpp:279-303).  A segment whose haplotypes can hold any other character (IUPAC
 			// codes in the FASTA, in an inserted sequence or in an allele) keeps its strings on the host and gets its GC
 			// percentages from gc_percent() below.
-			bool exotic = fasta.other_in(refOff, refOff + refLen);
+			bool exotic = needHost && fasta.other_in(refOff, refOff + refLen);
 			if (!exotic && useRefBuild && refLen > 0 && segment_is_copy_only(v[k], popu)) {
 				segment_copies_and_pokes(v[k], popu, reps[k], pokes[k]);
 				for (const Poke& pk : pokes[k]) exotic |= !is_acgtn(pk.c);
@@ -401,6 +422,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 					continue;
 				}
 			}
+			if (!needHost) fasta.chromosome(chr);          // (an exotic allele on a chromosome that was not needed on the host so far)
 			build_haplotypes(v[k], popu, haps[k]);
 			for (int h = 0; h < ploidy; h++) {
 				L.hapLen[k][h] = haps[k][h].size();
@@ -409,7 +431,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 			hostGc[k] = exotic ? 1 : 0;
 		}
 		double t1 = PhaseTimers::now();
-		if (anyDev)
+		if (anyDev && !devRef)
 			for (ssc_handle* dev : devs) { rc = ssc_reference_upload(dev, chrSeq.data(), chrSeq.size()); if (rc) return rc; }
 		std::vector<int64_t> pokePos; std::vector<char> pokeChr;
 		for (int h = 0; h < ploidy; h++) {
@@ -612,6 +634,7 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 		double tc0 = PhaseTimers::now();
 		set_read_counts(popu, pp.second);
 		g_tm.counts += PhaseTimers::now() - tc0;
+		const double tf0 = PhaseTimers::now();
 		for (auto& chr : chroms) {
 			std::vector<Segment>& v = segs[popu][chr];
 			const int32_t nameOff = (int32_t)names.size();
@@ -691,10 +714,8 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 				}
 			}
 		}
+		g_tm.flatten += PhaseTimers::now() - tf0;
 	}
-	if (getenv("SIMUSCOP_TIMING"))
-		fprintf(stderr, "[simuscop timing] haplotypes %.2f s, upload+pack %.2f s, gc census (device, incl. bin enumeration %.2f s) %.2f s, gc weights (host) %.2f s, read counts %.2f s\n",
-		        g_tm.build, g_tm.upload, g_tm.enumerate, g_tm.census, g_tm.gc, g_tm.counts);
 	if (pw.fp && flatDump) {
 		pw.rec(5, std::string((const char*)bins.data(), bins.size() * sizeof(ssc_bin)));
 		pw.rec(6, std::string((const char*)segments.data(), segments.size() * sizeof(ssc_segment)));
@@ -702,11 +723,17 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 	}
 	if (pw.fp) { pw.rec(9, std::string()); fclose(pw.fp); }
 	if (devs.empty()) { if (planned) *planned = 0; if (emitted) *emitted = 0; return 0; }
+	const double ts0 = PhaseTimers::now();
 	for (ssc_handle* dev : devs) {
 		rc = ssc_set_plan(dev, seed, bins.data(), (int64_t)bins.size(), segments.data(), (int64_t)segments.size(),
 		                  names.data(), (int64_t)names.size(), planned, emitted);
 		if (rc) return rc;
 	}
+	g_tm.setPlan += PhaseTimers::now() - ts0;
+	if (getenv("SIMUSCOP_TIMING"))
+		fprintf(stderr, "[simuscop timing] reference upload / haplotype strings %.2f s, append+pack %.2f s, gc census (device, incl. bin enumeration %.2f s) %.2f s, "
+		                "gc weights (host) %.2f s, read counts %.2f s, flat bins %.2f s, ssc_set_plan %.2f s (%lld bins)\n",
+		        g_tm.build, g_tm.upload, g_tm.enumerate, g_tm.census, g_tm.gc, g_tm.counts, g_tm.flatten, g_tm.setPlan, (long long)bins.size());
 	return 0;
 }
 

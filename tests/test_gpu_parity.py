@@ -364,3 +364,52 @@ def test_device_built_haplotypes_equal_host_strings(name, built, workdir):
     finally:
         g.close()
         job.close()
+
+
+def test_fasta_record_unfolded_on_the_device(built, tmp_path):
+    """ssc_reference_upload_fasta: the sequence lines of a FASTA record read from the file descriptor and unfolded on the GPU
+    (line ends dropped, upper-cased) equal the host's chromosome string, for several line geometries (60 / 7 / 1000 columns,
+    CR-LF line ends, a last line with and without terminator, a record in the middle of the file), and the count of characters
+    that are neither ACGT nor N is exact."""
+    import ctypes as C
+    import os
+    import numpy as np
+    from simuscop_b200 import cuda_binding
+    rng = np.random.default_rng(17)
+    L = cuda_binding.lib()
+    scn = helpers.build_stress("k3_rl95", str(tmp_path))
+    plans, _ = helpers.run_reference_philox(scn, tag="uf")
+    plan = planfile.read_plan(plans[0])
+    g = cuda_binding.Generator(0)
+    try:
+        g.load_plan(plan, scn["seed"])                       # a profile must be set (base order of the packed codes)
+        for cols, eol, n, tail_eol in ((60, b"\n", 100000, True), (7, b"\n", 1234, False), (1000, b"\r\n", 2501, True),
+                                       (60, b"\n", 60, True), (61, b"\n", 1, False), (50, b"\n", 3000017, True)):
+            seq = np.frombuffer(b"ACGTacgtNnRYkm", np.uint8)[rng.integers(0, 14, n)]
+            body = b"".join(seq[i:i + cols].tobytes() + eol for i in range(0, n, cols))
+            if not tail_eol:
+                body = body[:-len(eol)]
+            head = b">first\nACGT\n>chrT some text\n"
+            path = str(tmp_path / ("g_%d_%d.fa" % (cols, n)))
+            with open(path, "wb") as f:
+                f.write(head + body + (b"\n>after\nGGGG\n" if tail_eol else b""))
+            lines = (n - 1) // cols
+            raw_len = n + lines * len(eol)
+            fd = os.open(path, os.O_RDONLY)
+            other = C.c_uint64()
+            try:
+                cuda_binding._ck(L.ssc_reference_upload_fasta(g.h, fd, len(head), raw_len, n, cols, cols + len(eol), C.byref(other)))
+            finally:
+                os.close(fd)
+            up = seq & 0xDF
+            is_acgtn = (up == 65) | (up == 67) | (up == 71) | (up == 84) | (up == 78)
+            assert other.value == int((~is_acgtn).sum())
+            cuda_binding._ck(L.ssc_genome_reserve(g.h, 2 * n + 64))
+            first = C.c_uint64()
+            cuda_binding._ck(L.ssc_genome_append_ref(g.h, 0, n, 2, C.byref(first)))
+            want = up.copy()
+            want[~((up == 65) | (up == 67) | (up == 71) | (up == 84))] = ord("N")
+            got = np.frombuffer(g.genome_read(0, 2 * n), np.uint8)
+            assert (got[:n] == want).all() and (got[n:] == want).all(), (cols, n)
+    finally:
+        g.close()

@@ -346,3 +346,35 @@ def test_gzip_member_host_mirror_inflates(built):
     buf = C.create_string_buffer(4 * len(noise))
     m = L.ssc_gzip_member_host(noise, len(noise), sample, len(sample), buf, len(buf))
     assert gzip.decompress(buf.raw[:m]) == noise
+
+
+def test_file_writer_sink_writes_ordered_slabs(built, tmp_path):
+    """The output side of the drop-in CLI (ssh_writer_*, the role of SeqWriter::write): slabs handed to the sink in order end
+    up back to back in the files, whatever the number of pwrite workers, for paired and single-end layouts."""
+    import numpy as np
+    from simuscop_b200 import abi, host_binding
+    hl = host_binding.lib()
+    hl.ssh_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    hl.ssh_writer_sink.restype = C.c_void_p
+    hl.ssh_writer_close.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    sink = C.cast(hl.ssh_writer_sink(), abi.SINK_FN)
+    rng = np.random.default_rng(3)
+    for threads, paired in ((1, True), (5, True), (3, False)):
+        p1, p2 = str(tmp_path / ("w%d_1.fq" % threads)), str(tmp_path / ("w%d_2.fq" % threads))
+        w = C.c_void_p()
+        assert hl.ssh_writer_open(p1.encode(), p2.encode() if paired else None, threads, C.byref(w)) == 0
+        want1, want2 = b"", b""
+        for n in (0, 1, 17, (8 << 20) - 1, (8 << 20) + 5, 20 << 20):          # around the 8 MiB chunk size of the pool
+            a = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            b = rng.integers(0, 256, n // 2 + 3, dtype=np.uint8).tobytes() if paired else b""
+            assert sink(w, a, len(a), b if paired else None, len(b), 0, 0) == 0
+            want1 += a; want2 += b
+        b1, b2 = C.c_uint64(), C.c_uint64()
+        assert hl.ssh_writer_close(w, C.byref(b1), C.byref(b2)) == 0
+        assert (b1.value, b2.value) == (len(want1), len(want2))
+        assert open(p1, "rb").read() == want1
+        if paired:
+            assert open(p2, "rb").read() == want2
+        else:
+            assert not os.path.exists(p2)
+    assert hl.ssh_writer_open(str(tmp_path / "no" / "such" / "dir.fq").encode(), None, 2, C.byref(C.c_void_p())) != 0
