@@ -72,6 +72,7 @@ struct ssc_handle {
 	bool forceGeneric = false;
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
+	bool carryPass2 = true;       // pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 (off: stand-alone kernel per batch)
 	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
 	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
 	ssc::GzTables* d_gzTab = nullptr;
@@ -323,9 +324,10 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
 			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, s, e0, e1));
 			CK(ssc::launch_scan_blobs(P, s));
-			if (e2) CK(cudaEventRecord(e2, s));
 			h->pending.P = P; h->pending.valid = true;
 			h->stats.launches += 2;
+			if (!h->carryPass2) { int rc = flush_pending(h); if (rc) return rc; }
+			if (e2) CK(cudaEventRecord(e2, s));
 		} else {
 			// gzip mode: blobs -> (first batch of a plan: fit the Huffman table to a sample) -> one gzip member per blob -> pass 2 on the members
 			int rc = flush_pending(h);
@@ -439,7 +441,9 @@ int ssc_destroy(ssc_handle* h) {
 		}
 		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
 		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
-		if (b == 0 && h->d_slots[0]) cudaFree(h->d_slots[0]);   // d_slots[1] points into the same allocation
+		if (h->d_slots[b][0]) cudaFree(h->d_slots[b][0]);       // d_slots[b][1] points into the same allocation
+		h->d_blobPrefix[b].release();
+		if (h->evDense[b]) cudaEventDestroy(h->evDense[b]);
 		if (h->d_result[b]) cudaFree(h->d_result[b]);
 		if (h->h_result[b]) cudaFreeHost(h->h_result[b]);
 		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();
@@ -477,6 +481,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 		return SSC_OK;
 	}
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
+	if (!strcmp(key, "carry_pass2")) { h->carryPass2 = value != 0; return SSC_OK; }
 	if (!strcmp(key, "max_ctas")) { if (value < 0) return fail(SSC_ERR_INVALID, "max_ctas must be >= 0"); h->maxCtas = (int)value; return SSC_OK; }
 	if (!strcmp(key, "no_splice")) { h->noSplice = value != 0; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
@@ -883,14 +888,16 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 	for (int64_t e = eLo; e < eHi; e += h->slabPairs) batches.push_back({e, std::min(eHi, e + h->slabPairs)});
 	const int nb = (int)batches.size();
 	// pipeline: the launch of batch k+1 (which also completes the dense slab of batch k) runs under the device->host copies of
-	// batch k (file 1 / file 2 on two streams), which run under the sink of batch k-1.  Slab hazards: the launch of batch k+1
-	// writes d_out[k & 1] (fused pass 2 of batch k) or d_out[(k+1) & 1] (other modes): the compute stream waits for every
-	// copy issued so far before it; h_out[k & 1] was consumed by the sink of batch k-2 an iteration ago.
+	// batch k-1 (file 1 / file 2 on two streams), which run under the sink of batch k-2.  h_out[k & 1] was consumed by the
+	// sink of batch k-2 an iteration before the copy of batch k is issued.
+	int qm = 0; size_t sb = 0;
+	const bool carried = use_fast(h, &qm, &sb) && !h->gzip && h->carryPass2;     // pass 2b of batch k rides on the launch of batch k+1
 	auto launch = [&](int k) -> int {
-		for (int b = 0; b < 2; b++) {
-			CK(cudaStreamWaitEvent(h->compute, h->evCopy[b], 0));
-			CK(cudaStreamWaitEvent(h->compute, h->evCopy2[b], 0));
-		}
+		// the dense slab this launch writes: d_out[(k-1) & 1] when it carries the previous batch's moves, else d_out[k & 1];
+		// its last reader is the copy of the batch two before the one that now lands there
+		const int target = carried ? (k + 1) & 1 : k & 1;
+		CK(cudaStreamWaitEvent(h->compute, h->evCopy[target], 0));
+		CK(cudaStreamWaitEvent(h->compute, h->evCopy2[target], 0));
 		int r = launch_batch(h, k & 1, batches[k].lo, batches[k].hi);
 		if (r) return r;
 		CK(cudaEventRecord(h->evGen[k & 1], h->compute));

@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(SC_THREADS) scan_blobs_kernel(const GenParams 
 }
 
 // pass 2b: blob j of a batch -> its place in the dense slabs (one warp)
-__device__ __forceinline__ void move_blob(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
+template <bool INL>
+__device__ __forceinline__ void move_blob_body(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
                                           const unsigned long long* __restrict__ tileState, const unsigned long long* __restrict__ prefix,
                                           uint8_t* __restrict__ dense1, uint8_t* __restrict__ dense2, unsigned long long cap1,
                                           unsigned long long cap2, int j, int lane) {
@@ -586,6 +587,20 @@ __device__ __forceinline__ void move_blob(const uint8_t* __restrict__ blobs1, co
 	const size_t blob = (size_t)j * blobPitch;
 	copy_realign(blobs1 + blob, l1, dense1 + d1, lane);
 	if (l2) copy_realign(blobs2 + blob, l2, dense2 + d2, lane);
+}
+__device__ __forceinline__ void move_blob(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
+                                          const unsigned long long* __restrict__ tileState, const unsigned long long* __restrict__ prefix,
+                                          uint8_t* __restrict__ dense1, uint8_t* __restrict__ dense2, unsigned long long cap1,
+                                          unsigned long long cap2, int j, int lane) {
+	move_blob_body<true>(blobs1, blobs2, blobPitch, tileState, prefix, dense1, dense2, cap1, cap2, j, lane);
+}
+// Out of line for the generation kernel: once per ticket, and its body must not sit between the hot loops of that kernel
+// (they have to stay in the instruction cache).
+__device__ __noinline__ void move_blob_call(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
+                                            const unsigned long long* __restrict__ tileState, const unsigned long long* __restrict__ prefix,
+                                            uint8_t* __restrict__ dense1, uint8_t* __restrict__ dense2, unsigned long long cap1,
+                                            unsigned long long cap2, int j, int lane) {
+	move_blob_body<false>(blobs1, blobs2, blobPitch, tileState, prefix, dense1, dense2, cap1, cap2, j, lane);
 }
 
 // stand-alone form: the last batch of a call (nothing follows that could carry its moves) and the gzip members
@@ -980,7 +995,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		// lies in HBM since the previous launch and its offset is final, so nothing is waited for; the loads are in flight
 		// while the other warps of the SM keep generating.
 		if (chunk < P.nTilesPrev)
-			move_blob(P.prevBlobs, P.prevBlobs + P.prevFile2Off, P.prevBlobPitch, P.prevTileState, P.prevPrefix, P.prevDense1, P.prevDense2,
+			move_blob_call(P.prevBlobs, P.prevBlobs + P.prevFile2Off, P.prevBlobPitch, P.prevTileState, P.prevPrefix, P.prevDense1, P.prevDense2,
 			          P.prevCap1, P.prevCap2, chunk, lane);
 	}
 

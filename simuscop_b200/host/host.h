@@ -132,7 +132,7 @@ public:
 	double weighted_length(Segment& seg, const std::string& popu);
 	double weighted_length_from(Segment& seg, const std::vector<std::string>& haps);
 	void enumerate_bins(const Segment& seg, const std::vector<size_t>& hapLen, std::vector<BinSpec>& out);
-	double weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc);
+	double weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc, const double* factors = nullptr);
 	// weights pass on the device (ssc_gc_census), streaming the haplotype store at the same time
 	int device_weights(const std::string& popu, const std::vector<ssc_handle*>& devs, uint64_t& localSize,
 	                   std::map<std::string, ChrLayout>& layout);

@@ -4,7 +4,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <iostream>
 
@@ -294,14 +296,16 @@ void Job::enumerate_bins(const Segment& seg, const std::vector<size_t>& hapLen, 
 }
 
 // weights of the enumerated bins from their GC percentages (one Profile::getGCFactor draw per bin, in bin order)
-double Job::weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc) {
+// factors (optional): the getGCFactor draw of every bin, made ahead in the same per-percentage order (device_weights)
+double Job::weights_from_gc(Segment& seg, const std::vector<BinSpec>& specs, const int* gc, const double* factors) {
 	const unsigned int fragSize = 1000;
 	double wl = 0;
+	seg.bins.reserve(seg.bins.size() + specs.size());
 	for (size_t b = 0; b < specs.size(); b++) {
 		const BinSpec& sp = specs[b];
 		double w;
-		if (sp.kind == 0) w = prof.gc_factor(gc[b]) / fragSize;
-		else if (sp.kind == 1) w = prof.gc_factor(gc[b]) * sp.n / (fragSize * fragSize);
+		if (sp.kind == 0) w = (factors ? factors[b] : prof.gc_factor(gc[b])) / fragSize;
+		else if (sp.kind == 1) w = (factors ? factors[b] : prof.gc_factor(gc[b])) * sp.n / (fragSize * fragSize);
 		else w = 0.0;
 		seg.bins.push_back(Bin{sp.spos, sp.epos, sp.hap, w, 0});
 		wl += w;
@@ -479,11 +483,18 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		rc = ssc_gc_census(devs[0], starts.data(), lens.data(), (int64_t)starts.size(), cgc.data(), cnn.data());
 		if (rc) return rc;
 		double t3 = PhaseTimers::now();
-		size_t q = 0;
-		std::vector<int> gc;
+		// GC percentage of every bin of the chromosome, then the getGCFactor draws.  Every percentage has its own engine
+		// (Profile.cpp:1409-1415), so the draws of one percentage only depend on the order of the bins with that percentage:
+		// the 101 streams are independent and are advanced by several threads, each stream in bin order -- the values are
+		// the ones a single pass over the bins would draw.
+		size_t q = 0, flat = 0;
+		std::vector<std::vector<int>> gcs(v.size());
+		std::vector<size_t> flatOff(v.size(), 0);
 		for (size_t k = 0; k < v.size(); k++) {
 			if (v[k].weighted) continue;
+			std::vector<int>& gc = gcs[k];
 			gc.assign(specs[k].size(), 0);
+			flatOff[k] = flat; flat += specs[k].size();
 			for (size_t b = 0; b < specs[k].size(); b++) {
 				if (specs[k][b].kind == 2) continue;
 				if (hostGc[k]) { gc[b] = gc_percent(haps[k][specs[k][b].hap].data() + specs[k][b].gcStart, (size_t)specs[k][b].gcLen); continue; }
@@ -492,7 +503,34 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 				gc[b] = n == 0 ? 0 : (cnn[q] > 0 ? -1 : 100 * cgc[q] / n);
 				q++;
 			}
-			weights_from_gc(v[k], specs[k], gc.data());
+		}
+		std::vector<double> factors(flat, 0.0);
+		{
+			std::vector<std::vector<uint32_t>> byGc(101);
+			for (size_t k = 0; k < v.size(); k++) {
+				if (v[k].weighted) continue;
+				for (size_t b = 0; b < specs[k].size(); b++) {
+					const int g = gcs[k][b];
+					if (specs[k][b].kind != 2 && g >= 0 && g <= 100) byGc[g].push_back((uint32_t)(flatOff[k] + b));
+				}
+			}
+			const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+			std::atomic<int> next(0);
+			auto run = [&]() {
+				for (int g = next.fetch_add(1); g <= 100; g = next.fetch_add(1))
+					for (uint32_t i : byGc[g]) factors[i] = prof.gc_factor(g);
+			};
+			if (flat < 20000 || T == 1) run();
+			else {
+				std::vector<std::thread> th;
+				for (unsigned t = 1; t < T; t++) th.emplace_back(run);
+				run();
+				for (auto& t : th) t.join();
+			}
+		}
+		for (size_t k = 0; k < v.size(); k++) {
+			if (v[k].weighted) continue;
+			weights_from_gc(v[k], specs[k], gcs[k].data(), factors.data() + flatOff[k]);
 		}
 		g_tm.build += t1 - t0; g_tm.upload += t2 - t1; g_tm.census += t3 - t2; g_tm.gc += PhaseTimers::now() - t3;
 	}
