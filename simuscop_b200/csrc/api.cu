@@ -10,7 +10,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/simuscop.h"
@@ -628,27 +630,38 @@ int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint
 	}
 	cudaStream_t s = h->compute;
 	CK(cudaMemsetAsync(h->d_other.p, 0, 8, s));
-	// file -> pinned staging (pread) -> device, two staging buffers in turn: the read of chunk k+1 runs under the DMA of chunk k
-	// (and under the pack kernels of the previous chromosome that are still queued on the stream)
-	uint64_t done = 0;
-	int k = 0;
-	while (done < raw_len) {
-		const size_t chunk = (size_t)std::min<uint64_t>(h->stageBytes, raw_len - done);
-		CK(cudaEventSynchronize(h->evStage[k]));           // staging buffer k free again
-		size_t got = 0;
-		while (got < chunk) {
-			const ssize_t r = pread(fd, h->h_stage[k] + got, chunk - got, (off_t)(file_offset + done + got));
-			if (r < 0) { if (errno == EINTR) continue; return fail(SSC_ERR_INVALID, "reading the FASTA file failed: %s", strerror(errno)); }
-			if (r == 0) break;                             // a last line without a line feed ends the file early
-			got += (size_t)r;
+	// file -> pinned staging (pread) -> device.  Two staging buffers, each fed by its own host thread (even / odd chunks): the
+	// page-cache copy of pread is the slow part, so two of them run at a time, under the DMA of earlier chunks (and under the
+	// pack kernels of the previous chromosome that are still queued on the stream).
+	const uint64_t nChunks = (raw_len + h->stageBytes - 1) / h->stageBytes;
+	int rcs[2] = {SSC_OK, SSC_OK};
+	std::string errMsg[2];
+	auto feed = [&](int k) {
+		if (cudaSetDevice(h->device) != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = "cudaSetDevice failed"; return; }
+		for (uint64_t c = (uint64_t)k; c < nChunks; c += 2) {
+			const uint64_t done = c * h->stageBytes;
+			const size_t chunk = (size_t)std::min<uint64_t>(h->stageBytes, raw_len - done);
+			cudaError_t e = cudaEventSynchronize(h->evStage[k]);          // staging buffer k free again
+			size_t got = 0;
+			while (e == cudaSuccess && got < chunk) {
+				const ssize_t r = pread(fd, h->h_stage[k] + got, chunk - got, (off_t)(file_offset + done + got));
+				if (r < 0) { if (errno == EINTR) continue; rcs[k] = SSC_ERR_INVALID; errMsg[k] = std::string("reading the FASTA file failed: ") + strerror(errno); return; }
+				if (r == 0) break;                                         // a last line without a line feed ends the file early
+				got += (size_t)r;
+			}
+			if (got < chunk) memset(h->h_stage[k] + got, '\n', chunk - got);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_raw.p + done, h->h_stage[k], chunk, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess) e = cudaEventRecord(h->evStage[k], s);
+			if (e != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = std::string("staging the FASTA record failed: ") + cudaGetErrorString(e); return; }
 		}
-		if (got < chunk) memset(h->h_stage[k] + got, '\n', chunk - got);
-		CK(cudaMemcpyAsync(h->d_raw.p + done, h->h_stage[k], chunk, cudaMemcpyHostToDevice, s));
-		CK(cudaEventRecord(h->evStage[k], s));
-		h->stats.h2d_bytes += chunk;
-		done += chunk;
-		k ^= 1;
-	}
+	};
+	if (nChunks > 1) {
+		std::thread other(feed, 1);
+		feed(0);
+		other.join();
+	} else feed(0);
+	for (int k = 0; k < 2; k++) if (rcs[k]) return fail(rcs[k], "%s", errMsg[k].c_str());
+	h->stats.h2d_bytes += raw_len;
 	CK(ssc::launch_unfold(h->d_raw.p, raw_len, n_bases, line_bases, line_width, h->d_ref.p, h->d_other.p, s));
 	unsigned long long other = 0;
 	CK(cudaMemcpyAsync(&other, h->d_other.p, 8, cudaMemcpyDeviceToHost, s));
@@ -756,15 +769,24 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	h->seed = seed;
 	h->havePlan = false;
 	h->haveGz = false;
+	h->pending.valid = false;
+
+	// The per-bin passes below run on a few host threads over contiguous bin / segment ranges (a 3 Gb diploid plan has
+	// 6 M bins); every result is position-determined, so the plan does not depend on the thread count.
+	const unsigned T = (unsigned)std::max<int64_t>(1, std::min<int64_t>({16, (int64_t)std::thread::hardware_concurrency(), n_bins / 65536 + 1}));
+	auto parallel = [&](int64_t n, const std::function<void(int64_t, int64_t, unsigned)>& fn) {
+		if (T == 1 || n < 2) { fn(0, n, 0); return; }
+		std::vector<std::thread> th;
+		for (unsigned k = 1; k < T; k++) th.emplace_back(fn, n * k / T, n * (k + 1) / T, k);
+		fn(0, n / T, 0);
+		for (auto& x : th) x.join();
+	};
 
 	// ---- validate, planned pairs, risky bins
 	std::vector<int64_t>& pb = h->planBaseAll;
 	pb.assign(n_bins + 1, 0);
 	std::vector<int32_t> planned(n_bins), emit(n_bins);
-	std::vector<ssc::CensusBin> census;
-	std::vector<int64_t> censusOf;            // census index -> bin
 	std::vector<int32_t> riskyBase(n_bins, -1);
-	int64_t riskyTotal = 0;
 	int maxName = 0;
 	if (names_len < 0 || names_len >= (1 << 17)) return fail(SSC_ERR_INVALID, "name blob of %lld bytes (limit 131071)", (long long)names_len);
 	for (int64_t s = 0; s < n_segs; s++) {
@@ -774,39 +796,54 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 			return fail(SSC_ERR_INVALID, "segment %lld: bad name (max 64 bytes)", (long long)s);
 		maxName = std::max(maxName, (int)segs[s].name_len);
 	}
-	for (int64_t i = 0; i < n_bins; i++) {
-		const ssc_bin& b = bins[i];
-		int64_t n = b.read_count > 0 ? (paired ? ((int64_t)b.read_count + 1) / 2 : (int64_t)b.read_count) : 0;
-		if (n > 0) {
-			if (b.segment < 0 || b.segment >= n_segs) return fail(SSC_ERR_INVALID, "bin %lld: bad segment", (long long)i);
-			if (b.spos < 0 || b.epos < b.spos) return fail(SSC_ERR_INVALID, "bin %lld: bad range", (long long)i);
-			if (b.segsize == 0) return fail(SSC_ERR_INVALID, "bin %lld: segsize 0 (copy number 0 segments cannot emit reads)", (long long)i);
-			if (b.hap_base < 0 || b.contig_end < b.hap_base || (uint64_t)b.contig_end > h->genomeSize)
-				return fail(SSC_ERR_INVALID, "bin %lld: haplotype range outside the store", (long long)i);
-			if (n > 0x7fffffff) return fail(SSC_ERR_INVALID, "bin %lld: too many reads", (long long)i);
-		}
-		planned[i] = (int32_t)n;
-		emit[i] = (int32_t)n;
-		pb[i + 1] = pb[i] + n;
-		if (n > 0) {
-			// an attempt fails iff min(want, contig_end - (hap_base+pos)) < RL  (Segment.cpp:753)
-			bool risky = (int64_t)b.epos > b.contig_end - b.hap_base - RL;
-			if (!paired && ((int64_t)b.epos - b.spos + 1) < RL) risky = true;
-			if (paired && t.nIsize == 0 && t.fixedInsert < RL) risky = true;
-			if (paired && t.nIsize > 0 && t.minIS < RL) risky = true;          // an insert-size table that reaches below the read length
-			if (risky) {
-				ssc::CensusBin c;
-				c.hap_base = b.hap_base + SSC_GPAD; c.contig_end = b.contig_end + SSC_GPAD; c.plan_base = pb[i];
-				c.spos = b.spos; c.epos = b.epos; c.planned = (int32_t)n; c.risky_base = (int32_t)riskyTotal;
-				if (riskyTotal + n > 0x7fffffff) return fail(SSC_ERR_INVALID, "too many pairs in bins that can fail");
-				riskyBase[i] = (int32_t)riskyTotal;
-				riskyTotal += n;
-				census.push_back(c);
-				censusOf.push_back(i);
+	struct BinError { int64_t bin = -1; const char* what = nullptr; };
+	std::vector<BinError> errs(T);
+	std::vector<std::vector<int64_t>> riskyOf(T);              // bins that can fail, per thread range (ascending)
+	parallel(n_bins, [&](int64_t lo, int64_t hi, unsigned tid) {
+		for (int64_t i = lo; i < hi; i++) {
+			const ssc_bin& b = bins[i];
+			const int64_t n = b.read_count > 0 ? (paired ? ((int64_t)b.read_count + 1) / 2 : (int64_t)b.read_count) : 0;
+			if (n > 0 && errs[tid].bin < 0) {
+				const char* what = nullptr;
+				if (b.segment < 0 || b.segment >= n_segs) what = "bad segment";
+				else if (b.spos < 0 || b.epos < b.spos) what = "bad range";
+				else if (b.segsize == 0) what = "segsize 0 (copy number 0 segments cannot emit reads)";
+				else if (b.hap_base < 0 || b.contig_end < b.hap_base || (uint64_t)b.contig_end > h->genomeSize) what = "haplotype range outside the store";
+				else if (n > 0x7fffffff) what = "too many reads";
+				if (what) { errs[tid].bin = i; errs[tid].what = what; }
+			}
+			planned[i] = (int32_t)n;
+			emit[i] = (int32_t)n;
+			if (n > 0) {
+				// an attempt fails iff min(want, contig_end - (hap_base+pos)) < RL  (Segment.cpp:753)
+				bool risky = (int64_t)b.epos > b.contig_end - b.hap_base - RL;
+				if (!paired && ((int64_t)b.epos - b.spos + 1) < RL) risky = true;
+				if (paired && t.nIsize == 0 && t.fixedInsert < RL) risky = true;
+				if (paired && t.nIsize > 0 && t.minIS < RL) risky = true;          // an insert-size table that reaches below the read length
+				if (risky) riskyOf[tid].push_back(i);
 			}
 		}
-	}
+	});
+	for (unsigned k = 0; k < T; k++)
+		if (errs[k].bin >= 0) return fail(SSC_ERR_INVALID, "bin %lld: %s", (long long)errs[k].bin, errs[k].what);
+	for (int64_t i = 0; i < n_bins; i++) pb[i + 1] = pb[i] + planned[i];
 	h->plannedPairs = pb[n_bins];
+	std::vector<ssc::CensusBin> census;
+	std::vector<int64_t> censusOf;            // census index -> bin
+	int64_t riskyTotal = 0;
+	for (unsigned k = 0; k < T; k++)
+		for (int64_t i : riskyOf[k]) {
+			const ssc_bin& b = bins[i];
+			const int64_t n = planned[i];
+			ssc::CensusBin c;
+			c.hap_base = b.hap_base + SSC_GPAD; c.contig_end = b.contig_end + SSC_GPAD; c.plan_base = pb[i];
+			c.spos = b.spos; c.epos = b.epos; c.planned = (int32_t)n; c.risky_base = (int32_t)riskyTotal;
+			if (riskyTotal + n > 0x7fffffff) return fail(SSC_ERR_INVALID, "too many pairs in bins that can fail");
+			riskyBase[i] = (int32_t)riskyTotal;
+			riskyTotal += n;
+			census.push_back(c);
+			censusOf.push_back(i);
+		}
 
 	// ---- census on the device
 	cudaStream_t s = h->compute;
@@ -830,33 +867,53 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	eb.assign(n_bins + 1, 0);
 	for (int64_t i = 0; i < n_bins; i++) eb[i + 1] = eb[i] + emit[i];
 	h->emittedPairs = eb[n_bins];
-	std::vector<ssc::DevBin> dev;
-	std::vector<int64_t> devEmitBase;
-	dev.reserve(n_bins);
-	for (int64_t sIdx = 0; sIdx < n_segs; sIdx++) {
-		int64_t fragBase = 0;
-		for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
-			if (emit[i] > 0) {
-				if (bins[i].segment != sIdx) return fail(SSC_ERR_INVALID, "bin %lld does not belong to segment %lld", (long long)i, (long long)sIdx);
-				if (fragBase + emit[i] > 0x7fffffff) return fail(SSC_ERR_INVALID, "segment %lld: fragment counter overflow", (long long)sIdx);
-				ssc::DevBin d;
-				d.hap_base = bins[i].hap_base + SSC_GPAD; d.contig_end = bins[i].contig_end + SSC_GPAD;
-				d.plan_base = pb[i]; d.emit_base = eb[i];
-				d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
-				d.frag_base = (int32_t)fragBase;
-				d.name_off = segs[sIdx].name_offset; d.name_len = segs[sIdx].name_len;
-				d.risky_base = riskyBase[i]; d.pad = 0;
-				dev.push_back(d);
-				devEmitBase.push_back(eb[i]);
+	// device bins of segment sIdx go to dev[segOff[sIdx] ...): bins must be listed segment by segment in order, otherwise
+	// emit order != bin order
+	std::vector<int64_t> segOff(n_segs + 1, 0);
+	std::vector<const char*> segErr(T, nullptr);
+	std::vector<int64_t> segErrAt(T, -1);
+	parallel(n_segs, [&](int64_t lo, int64_t hi, unsigned tid) {
+		for (int64_t sIdx = lo; sIdx < hi; sIdx++) {
+			int64_t cnt = 0, fragBase = 0;
+			for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
+				if (emit[i] > 0) {
+					cnt++;
+					if (segErrAt[tid] < 0 && bins[i].segment != sIdx) { segErrAt[tid] = i; segErr[tid] = "does not belong to the segment that lists it"; }
+					if (segErrAt[tid] < 0 && fragBase + emit[i] > 0x7fffffff) { segErrAt[tid] = i; segErr[tid] = "fragment counter overflow of its segment"; }
+				}
+				fragBase += emit[i];
 			}
-			fragBase += emit[i];
+			segOff[sIdx + 1] = cnt;
 		}
-	}
-	// bins must be listed segment by segment in order, otherwise emit order != bin order
-	for (size_t k = 1; k < devEmitBase.size(); k++)
+	});
+	for (unsigned k = 0; k < T; k++) if (segErrAt[k] >= 0) return fail(SSC_ERR_INVALID, "bin %lld %s", (long long)segErrAt[k], segErr[k]);
+	for (int64_t sIdx = 0; sIdx < n_segs; sIdx++) segOff[sIdx + 1] += segOff[sIdx];
+	std::vector<ssc::DevBin> dev((size_t)segOff[n_segs]);
+	std::vector<int64_t>& devEmitBase = h->devEmitBase;
+	devEmitBase.assign((size_t)segOff[n_segs] + 1, 0);
+	parallel(n_segs, [&](int64_t lo, int64_t hi, unsigned) {
+		for (int64_t sIdx = lo; sIdx < hi; sIdx++) {
+			int64_t fragBase = 0, o = segOff[sIdx];
+			for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
+				if (emit[i] > 0) {
+					ssc::DevBin d;
+					d.hap_base = bins[i].hap_base + SSC_GPAD; d.contig_end = bins[i].contig_end + SSC_GPAD;
+					d.plan_base = pb[i]; d.emit_base = eb[i];
+					d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
+					d.frag_base = (int32_t)fragBase;
+					d.name_off = segs[sIdx].name_offset; d.name_len = segs[sIdx].name_len;
+					d.risky_base = riskyBase[i]; d.pad = 0;
+					dev[(size_t)o] = d;
+					devEmitBase[(size_t)o] = eb[i];
+					o++;
+				}
+				fragBase += emit[i];
+			}
+		}
+	});
+	devEmitBase[(size_t)segOff[n_segs]] = h->emittedPairs;
+	for (size_t k = 1; k + 1 < devEmitBase.size(); k++)
 		if (devEmitBase[k] <= devEmitBase[k - 1]) return fail(SSC_ERR_INVALID, "segments must list their bins in increasing, non-overlapping order");
-	devEmitBase.push_back(h->emittedPairs);
-	h->devEmitBase = devEmitBase;
 	h->nDevBins = (int64_t)dev.size();
 	CK(h->d_bins.upload(dev, s));
 	CK(h->d_emitBase.upload(devEmitBase, s));

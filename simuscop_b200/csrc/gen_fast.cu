@@ -498,11 +498,13 @@ __device__ __forceinline__ void emit_mapped(const WarpCtx& w, const IndelPlan& p
 // ---------------------------------------------------------------------------------------------
 // blob -> dense slab (the ordered write-out, done by the generating warps with a lag)
 // ---------------------------------------------------------------------------------------------
-// copy len bytes from a 16-byte aligned global source to an arbitrarily aligned global destination, 16-byte stores
+// copy len bytes from a 16-byte aligned global source to an arbitrarily aligned global destination, 16-byte stores.
+// Streaming accesses (ld.global.cs / st.global.cs): the blob is read once and the slab is not read again on the device, and
+// when the moves ride on a generation kernel they must not push the haplotype windows of that kernel out of the L2.
 __device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, int len, uint8_t* __restrict__ dst, int lane) {
 	int head = (int)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
 	if (head > len) head = len;
-	if (lane < head) dst[lane] = __ldcg(src + lane);
+	if (lane < head) dst[lane] = __ldcs(src + lane);
 	const int nvec = (len - head) >> 4;
 	const uint32_t* s32 = (const uint32_t*)src;
 	const int r8 = (head & 3) * 8;
@@ -511,16 +513,16 @@ __device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, in
 #pragma unroll 4
 	for (int v = lane; v < nvec; v += 32) {
 		const int q = q0 + 4 * v;
-		const uint32_t w0 = __ldcg(s32 + q), w1 = __ldcg(s32 + q + 1), w2 = __ldcg(s32 + q + 2), w3 = __ldcg(s32 + q + 3), w4 = __ldcg(s32 + q + 4);
+		const uint32_t w0 = __ldcs(s32 + q), w1 = __ldcs(s32 + q + 1), w2 = __ldcs(s32 + q + 2), w3 = __ldcs(s32 + q + 3), w4 = __ldcs(s32 + q + 4);
 		uint4 o;
 		o.x = __funnelshift_r(w0, w1, r8);
 		o.y = __funnelshift_r(w1, w2, r8);
 		o.z = __funnelshift_r(w2, w3, r8);
 		o.w = __funnelshift_r(w3, w4, r8);
-		dv[v] = o;
+		__stcs(dv + v, o);
 	}
 	const int t0 = head + (nvec << 4);
-	if (lane < len - t0) dst[t0 + lane] = __ldcg(src + t0 + lane);
+	if (lane < len - t0) dst[t0 + lane] = __ldcs(src + t0 + lane);
 }
 
 // pass 2a: exclusive prefix of the packed blob lengths (len1 << 31 | len2; a slab holds < 2^31 bytes), one CTA,
@@ -751,6 +753,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		if (lane == 0) chunk = (int)atomicAdd(P.ticket2, 1u);
 		chunk = __shfl_sync(0xffffffffu, chunk, 0);
 		if (chunk >= P.nLoop) break;
+		bool moved = false;
 		if (chunk < P.nTiles) {
 		// slot = pair index inside the batch (a batch has < 2^31 / FG_SLOT pairs)
 		const uint32_t slot0 = (uint32_t)chunk * FG_CHUNK;
@@ -817,6 +820,15 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 #pragma unroll 1
 		for (int p = 0; p < count; p++) {
+			// ---- pass 2 of the previous batch, carried by this launch: blob `chunk` of that batch to its dense place.  The blob
+			// lies in HBM since the previous launch and its offset is final, so nothing is waited for.  The warps of an SM run
+			// through their tickets almost in lock step; each one does its move in front of a different pair of its ticket
+			// (pair index = warp index), so that at any time only a few of them sit in the copy loop's memory latency.
+			if (p == warp && chunk < P.nTilesPrev) {
+				move_blob_call(P.prevBlobs, P.prevBlobs + P.prevFile2Off, P.prevBlobPitch, P.prevTileState, P.prevPrefix, P.prevDense1, P.prevDense2,
+				               P.prevCap1, P.prevCap2, chunk, lane);
+				moved = true;
+			}
 			w.c0 = __shfl_sync(0xffffffffu, k_pairLo, p); w.c1 = __shfl_sync(0xffffffffu, k_pairHi, p);
 			const uint32_t kg = __shfl_sync(0xffffffffu, k_g, p);
 			const uint32_t posmod = __shfl_sync(0xffffffffu, k_posmod, p), fragCount = __shfl_sync(0xffffffffu, k_frag, p);
@@ -991,12 +1003,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			}
 		}
 		}
-		// ---- pass 2 of the previous batch, carried by this launch: blob `chunk` of that batch to its dense place.  The blob
-		// lies in HBM since the previous launch and its offset is final, so nothing is waited for; the loads are in flight
-		// while the other warps of the SM keep generating.
-		if (chunk < P.nTilesPrev)
+		// (tickets shorter than the warp's phase, and tickets beyond this batch's own when the previous batch had more)
+		if (!moved && chunk < P.nTilesPrev)
 			move_blob_call(P.prevBlobs, P.prevBlobs + P.prevFile2Off, P.prevBlobPitch, P.prevTileState, P.prevPrefix, P.prevDense1, P.prevDense2,
-			          P.prevCap1, P.prevCap2, chunk, lane);
+			               P.prevCap1, P.prevCap2, chunk, lane);
 	}
 
 }

@@ -1,5 +1,6 @@
 // host_capi.cpp -- C ABI of include/simuscop_host.h and the file sink of the drop-in run.
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <cstdio>
@@ -34,10 +35,10 @@ struct ssh_writer {
 	std::vector<std::thread> pool;
 	std::mutex mu;
 	std::condition_variable cvWork, cvDone;
-	struct Chunk { int fd; const char* p; size_t n; uint64_t off; };
+	struct Chunk { int fd; const char* p; size_t n; uint64_t off; char* dst; };   // dst != nullptr: copy into the mapped file
 	std::vector<Chunk> queue;
 	size_t next = 0, inFlight = 0;
-	bool stop = false;
+	bool stop = false, noMap = false;
 	int err = 0;
 	// turnstile for several producers (one per GPU) that deliver batches out of order: batch k is written when every
 	// batch before it has been
@@ -52,6 +53,18 @@ struct ssh_writer {
 		}
 		return 0;
 	}
+	static int put(const Chunk& c) {
+		if (!c.dst) return pwrite_all(c.fd, c.p, c.n, c.off);
+#ifdef MADV_POPULATE_WRITE
+		// fault the chunk's pages in one call (page-aligned interior) instead of one trap per page
+		{
+			const uintptr_t a = ((uintptr_t)c.dst + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)c.dst + c.n) & ~(uintptr_t)4095;
+			if (b > a) madvise((void*)a, b - a, MADV_POPULATE_WRITE);
+		}
+#endif
+		memcpy(c.dst, c.p, c.n);
+		return 0;
+	}
 	void worker() {
 		std::unique_lock<std::mutex> lk(mu);
 		while (true) {
@@ -60,31 +73,47 @@ struct ssh_writer {
 			const Chunk c = queue[next++];
 			inFlight++;
 			lk.unlock();
-			const int e = pwrite_all(c.fd, c.p, c.n, c.off);
+			const int e = put(c);
 			lk.lock();
 			if (e && !err) err = e;
 			inFlight--;
 			if (next >= queue.size() && inFlight == 0) cvDone.notify_all();
 		}
 	}
-	// both slabs to their files at the running offsets; returns when written
+	// Both slabs to their files at the running offsets; returns when written.  With worker threads the file is extended and
+	// the slab's range mapped (MAP_SHARED): the workers copy their chunks into the mapping, which scales with the threads --
+	// buffered pwrite()s to ONE file serialise on its inode lock, so a pool of them writes no faster than two threads.
+	// Where the mapping fails (not a regular file) the chunks are pwrite()n.
 	int write_slabs(const char* b1, size_t l1, const char* b2, size_t l2) {
 		static const size_t CH = 8u << 20;
 		std::unique_lock<std::mutex> lk(mu);
 		queue.clear(); next = 0;
 		const char* bufs[2] = {b1, b2}; const size_t lens[2] = {l1, fd[1] >= 0 ? l2 : 0};
+		void* maps[2] = {nullptr, nullptr}; size_t mapLen[2] = {0, 0};
 		for (int f = 0; f < 2; f++) {
-			for (size_t o = 0; o < lens[f]; o += CH) queue.push_back(Chunk{fd[f], bufs[f] + o, std::min(CH, lens[f] - o), off[f] + o});
+			if (!lens[f]) continue;
+			char* base = nullptr;
+			if (!pool.empty() && !noMap) {
+				const uint64_t a = off[f] & ~(uint64_t)4095;
+				if (ftruncate(fd[f], (off_t)(off[f] + lens[f])) == 0) {
+					void* m = mmap(nullptr, (size_t)(off[f] + lens[f] - a), PROT_READ | PROT_WRITE, MAP_SHARED, fd[f], (off_t)a);
+					if (m != MAP_FAILED) { maps[f] = m; mapLen[f] = (size_t)(off[f] + lens[f] - a); base = (char*)m + (off[f] - a); }
+					else noMap = true;
+				} else noMap = true;
+			}
+			for (size_t o = 0; o < lens[f]; o += CH)
+				queue.push_back(Chunk{fd[f], bufs[f] + o, std::min(CH, lens[f] - o), off[f] + o, base ? base + o : nullptr});
 			off[f] += lens[f];
 		}
 		if (queue.empty()) return 0;
 		if (pool.empty()) {           // single-threaded: write here
-			for (const Chunk& c : queue) { const int e = pwrite_all(c.fd, c.p, c.n, c.off); if (e && !err) err = e; }
+			for (const Chunk& c : queue) { const int e = put(c); if (e && !err) err = e; }
 			queue.clear();
 			return err;
 		}
 		cvWork.notify_all();
 		cvDone.wait(lk, [&] { return next >= queue.size() && inFlight == 0; });
+		for (int f = 0; f < 2; f++) if (maps[f]) munmap(maps[f], mapLen[f]);
 		return err;
 	}
 };

@@ -673,6 +673,11 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 		set_read_counts(popu, pp.second);
 		g_tm.counts += PhaseTimers::now() - tc0;
 		const double tf0 = PhaseTimers::now();
+		{
+			size_t nb = bins.size(), ns = segments.size();
+			for (auto& chr : chroms) { ns += segs[popu][chr].size(); for (auto& sg : segs[popu][chr]) nb += sg.bins.size(); }
+			bins.reserve(nb); segments.reserve(ns);
+		}
 		for (auto& chr : chroms) {
 			std::vector<Segment>& v = segs[popu][chr];
 			const int32_t nameOff = (int32_t)names.size();
