@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--ref-slice-mb", type=int, default=0, help="--impl reference: size of the one-chromosome slice (default max(320, 16 x threads))")
     ap.add_argument("--file-dirs", default="/dev/shm,workdir", help="directories the e2e_file legs write to (workdir = --workdir)")
     ap.add_argument("--writer-threads", type=int, default=8)
+    ap.add_argument("--opts", default="", help="experiments: comma-separated ssc_set_option settings, e.g. carry_pass2=0,prefetch_windows=0")
+    ap.add_argument("--device-only", action="store_true", help="experiments: only the device-resident leg")
     ap.add_argument("--cli-wall", action="store_true", help="also time the drop-in CLI on the whole job (plain FASTQ to /dev/shm when it fits, gzip to --workdir)")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -288,6 +290,8 @@ def main():
 
     gen = cuda_binding.Generator(local)
     gen.set_option("batch_pairs", a.batch_pairs)
+    for kv in filter(None, a.opts.split(",")):
+        gen.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.perf_counter()
     planned, emitted = job.prepare(0, gen)
     t_plan = time.perf_counter() - t0
@@ -327,6 +331,14 @@ def main():
     st = gen.stats()
     dev_ms = st["device_ms"]
     steps_done = a.steps
+
+    if a.device_only:
+        if rank == 0:
+            nbt = max(1, st["timed_batches"])
+            print(json.dumps({"opts": a.opts, "value": bases / dt, "ms_per_step": 1000.0 * dt / a.steps, "gen_ms": st["gen_kernel_ms"] / nbt,
+                              "pass2_ms": st["compact_kernel_ms"] / nbt, "profile": a.profile}))
+        gen.close(); job.close()
+        return 0
 
     # ---------------- the issue ceiling of this GPU (csrc/floor.cu): Philox only, and Philox + the fast per-base path
     floor = None
@@ -381,15 +393,6 @@ def main():
                     raise RuntimeError("only %.1f GB free, %.1f GB needed" % (free / 1e9, need / 1e9))
                 p1 = os.path.join(d, "simuscop_bench_r%d_1.fq" % rank)
                 p2 = os.path.join(d, "simuscop_bench_r%d_2.fq" % rank)
-                # warm-up pass = the same volume into the same files through a writer of its own: on a fresh VM the first touch of
-                # every page of host memory (page cache / tmpfs) costs a hypervisor fault; the timed pass (files truncated and
-                # written again) then runs at the rate of a box that has been up for a while
-                w = C.c_void_p()
-                if hl.ssh_writer_open(p1.encode(), p2.encode(), a.writer_threads, C.byref(w)):
-                    raise RuntimeError("cannot create %s" % p1)
-                for rg in spans(base_k + min(a.warmup, 3), a.steps):
-                    gen.generate(*rg, sink=sink_ptr, user=w)
-                hl.ssh_writer_close(w, None, None)
                 w = C.c_void_p()
                 if hl.ssh_writer_open(p1.encode(), p2.encode(), a.writer_threads, C.byref(w)):
                     raise RuntimeError("cannot create %s" % p1)

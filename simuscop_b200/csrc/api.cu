@@ -74,6 +74,7 @@ struct ssc_handle {
 	bool forceGeneric = false;
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
+	bool prefetchWindows = true;  // the ticket prologue of the fast kernel prefetches its pairs' haplotype windows into the L2
 	bool carryPass2 = true;       // pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 (off: stand-alone kernel per batch)
 	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
 	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
@@ -295,6 +296,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 		P.rk[2 * r + 1] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
 	}
 	P.tileStartBin = h->d_tileStart[buf].p; P.nTiles = nTiles; P.nLoop = nTiles; P.nTilesPrev = 0;
+	P.prefetchWindows = h->prefetchWindows ? 1 : 0;
 	P.tileState = h->d_tileState[buf].p; P.ticket = h->d_ticket[buf].p; P.ticket2 = h->d_ticket2.p; P.blobPrefix = h->d_blobPrefix[buf].p;
 	P.out1 = h->d_out[buf][0]; P.out2 = h->d_out[buf][1];
 	P.cap1 = h->slabCap; P.cap2 = h->slabCap;
@@ -484,6 +486,7 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 	}
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
 	if (!strcmp(key, "carry_pass2")) { h->carryPass2 = value != 0; return SSC_OK; }
+	if (!strcmp(key, "prefetch_windows")) { h->prefetchWindows = value != 0; return SSC_OK; }
 	if (!strcmp(key, "max_ctas")) { if (value < 0) return fail(SSC_ERR_INVALID, "max_ctas must be >= 0"); h->maxCtas = (int)value; return SSC_OK; }
 	if (!strcmp(key, "no_splice")) { h->noSplice = value != 0; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }

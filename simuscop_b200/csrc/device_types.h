@@ -88,6 +88,7 @@ struct GenParams {
 	// fast kernel, pass 2 folded into the next launch: while a warp generates ticket j of this batch it also moves blob j of
 	// the PREVIOUS batch (lengths and offsets final since that batch's scan) to its place in that batch's dense slab.
 	// nTilesPrev == 0: nothing to move; nLoop = max(nTiles, nTilesPrev) tickets are handed out.
+	int prefetchWindows;                // fast kernel: the ticket prologue pulls the windows of its 32 pairs into the L2
 	int nTilesPrev, nLoop;
 	const uint8_t* prevBlobs; uint32_t prevFile2Off; uint32_t prevBlobPitch;
 	const unsigned long long* prevTileState; const unsigned long long* prevPrefix;

@@ -498,10 +498,30 @@ __device__ __forceinline__ void emit_mapped(const WarpCtx& w, const IndelPlan& p
 // ---------------------------------------------------------------------------------------------
 // blob -> dense slab (the ordered write-out, done by the generating warps with a lag)
 // ---------------------------------------------------------------------------------------------
-// copy len bytes from a 16-byte aligned global source to an arbitrarily aligned global destination, 16-byte stores.
-// Streaming accesses (ld.global.cs / st.global.cs): the blob is read once and the slab is not read again on the device, and
-// when the moves ride on a generation kernel they must not push the haplotype windows of that kernel out of the L2.
-__device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, int len, uint8_t* __restrict__ dst, int lane) {
+// copy len bytes from a 16-byte aligned global source to an arbitrarily aligned global destination with 16-byte stores.
+// Vector v of the destination (16-byte aligned) takes source bytes [head + 16 v, head + 16 v + 16): two aligned 16-byte loads
+// (chunks v and v + 1 of the source) and four funnel shifts; the word offset head >> 2 of the window inside the chunk pair is
+// the same for the whole copy, so the loop exists once per offset (Q0).  Streaming accesses (ld.global.cs / st.global.cs): the
+// blob is read once and the slab is not read again on the device, and when the moves ride on a generation kernel they must
+// not push the haplotype windows of that kernel out of the L2.  The source may be read up to 16 bytes past len (blob pitch).
+template <int Q0, int U>
+__device__ __forceinline__ void copy_vectors(const uint4* __restrict__ s16, uint4* __restrict__ dv, int nvec, int r8, int lane) {
+#pragma unroll U
+	for (int v = lane; v < nvec; v += 32) {
+		const uint4 A = __ldcs(s16 + v), B = __ldcs(s16 + v + 1);
+		const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+		uint4 o;
+		o.x = __funnelshift_r(w[Q0], w[Q0 + 1], r8);
+		o.y = __funnelshift_r(w[Q0 + 1], w[Q0 + 2], r8);
+		o.z = __funnelshift_r(w[Q0 + 2], w[Q0 + 3], r8);
+		o.w = __funnelshift_r(w[Q0 + 3], w[Q0 + 4], r8);
+		__stcs(dv + v, o);
+	}
+}
+
+// The stand-alone move kernel keeps the first form of the copy (five 4-byte loads per vector, 32 registers, 8 CTAs per SM:
+// 5.15 TB/s of DRAM traffic); the two-16-byte-loads form above needs more registers than that kernel has.
+__device__ __forceinline__ void copy_realign_w32(const uint8_t* __restrict__ src, int len, uint8_t* __restrict__ dst, int lane) {
 	int head = (int)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
 	if (head > len) head = len;
 	if (lane < head) dst[lane] = __ldcs(src + lane);
@@ -520,6 +540,25 @@ __device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, in
 		o.z = __funnelshift_r(w2, w3, r8);
 		o.w = __funnelshift_r(w3, w4, r8);
 		__stcs(dv + v, o);
+	}
+	const int t0 = head + (nvec << 4);
+	if (lane < len - t0) dst[t0 + lane] = __ldcs(src + t0 + lane);
+}
+
+template <int U>
+__device__ __forceinline__ void copy_realign(const uint8_t* __restrict__ src, int len, uint8_t* __restrict__ dst, int lane) {
+	int head = (int)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+	if (head > len) head = len;
+	if (lane < head) dst[lane] = __ldcs(src + lane);
+	const int nvec = (len - head) >> 4;
+	const int r8 = (head & 3) * 8;
+	const uint4* s16 = (const uint4*)src;
+	uint4* dv = (uint4*)(dst + head);
+	switch (head >> 2) {
+	case 0: copy_vectors<0, U>(s16, dv, nvec, r8, lane); break;
+	case 1: copy_vectors<1, U>(s16, dv, nvec, r8, lane); break;
+	case 2: copy_vectors<2, U>(s16, dv, nvec, r8, lane); break;
+	default: copy_vectors<3, U>(s16, dv, nvec, r8, lane); break;
 	}
 	const int t0 = head + (nvec << 4);
 	if (lane < len - t0) dst[t0 + lane] = __ldcs(src + t0 + lane);
@@ -587,8 +626,13 @@ __device__ __forceinline__ void move_blob_body(const uint8_t* __restrict__ blobs
 	const int l1 = (int)(mine >> 31), l2 = (int)(mine & 0x7fffffffull);
 	if (d1 + (unsigned)l1 > cap1 || d2 + (unsigned)l2 > cap2) return;   // flagged by the scan
 	const size_t blob = (size_t)j * blobPitch;
-	copy_realign(blobs1 + blob, l1, dense1 + d1, lane);
-	if (l2) copy_realign(blobs2 + blob, l2, dense2 + d2, lane);
+	if (INL) {
+		copy_realign_w32(blobs1 + blob, l1, dense1 + d1, lane);
+		if (l2) copy_realign_w32(blobs2 + blob, l2, dense2 + d2, lane);
+	} else {
+		copy_realign<4>(blobs1 + blob, l1, dense1 + d1, lane);
+		if (l2) copy_realign<4>(blobs2 + blob, l2, dense2 + d2, lane);
+	}
 }
 __device__ __forceinline__ void move_blob(const uint8_t* __restrict__ blobs1, const uint8_t* __restrict__ blobs2, uint32_t blobPitch,
                                           const unsigned long long* __restrict__ tileState, const unsigned long long* __restrict__ prefix,
@@ -812,6 +856,17 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			const int64_t g0b = fstart + flen - RL;
 			const int64_t g0a = seReverse ? g0b : fstart;
 			k_winA = (uint32_t)((uint64_t)(g0a - 32) >> 4); k_winB = (uint32_t)((uint64_t)(g0b - 32) >> 4);
+			// The windows of the ticket's 32 pairs are scattered over a store of several GB; the pair loop gets to pair p only
+			// p x ~8 us from now.  Pulling the lines into the L2 here turns the HBM latency of every pair's window fetch (which the
+			// ~250 instructions between the cp.async and its wait do not cover) into an L2 hit.
+			if (lane < count && P.prefetchWindows) {
+				const uint32_t* dA = P.hap2 + k_winA; const uint32_t* mA = P.hapN + (k_winA >> 1);
+				const uint32_t* dB = P.hap2 + k_winB; const uint32_t* mB = P.hapN + (k_winB >> 1);
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(dA)); asm volatile("prefetch.global.L2 [%0];" ::"l"(dA + 15));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(mA)); asm volatile("prefetch.global.L2 [%0];" ::"l"(mA + 8));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(dB)); asm volatile("prefetch.global.L2 [%0];" ::"l"(dB + 15));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(mB)); asm volatile("prefetch.global.L2 [%0];" ::"l"(mB + 8));
+			}
 			k_g = ((uint32_t)g0a & 31u) | (((uint32_t)g0b & 31u) << 8) | (seReverse ? 0x80000000u : 0u);
 			k_posmod = posmod; k_frag = fragCount;
 			// name_off (17 bits) | name_len << 17 (7 bits) | digits of posmod << 24 | digits of fragCount << 28
