@@ -313,9 +313,7 @@ def main():
             first = (first + n) % nbatch
         return out
 
-    # ---------------- device-resident leg: ONE ssc_generate_device call over the K timed batches, outputs stay in HBM.
-    # (One call, not K: pass 2 of batch k -- moving its blobs into the dense ordered slab -- rides on the generation kernel of
-    # batch k+1, and the last batch's on a stand-alone kernel; all of it is inside the timed region.)
+    # ---------------- device-resident leg: ONE ssc_generate_device call over the K timed batches, outputs stay in HBM
     sampler = ClockSampler(local) if rank == 0 else None
     for rg in spans(0, a.warmup):
         gen.generate_device(*rg)
@@ -521,9 +519,8 @@ def main():
                                            "stores of an indel-free read"},
                          "ncu": ncu,
                          "note": "issue-bound kernel, not HBM-bound (DESIGN.md section 4).  kernel_ms_per_launch is the CUDA-event time "
-                                 "of generate_slots_kernel, which since round 2 also moves the previous batch's blobs into the dense "
-                                 "ordered slab (pass 2b); pass2_ms_per_launch = the scan of the blob lengths per batch + the one "
-                                 "stand-alone move of the call's last batch, spread over the batches"},
+                                 "of generate_slots_kernel (pass 1), pass2_ms_per_launch that of the scan of the blob lengths and the "
+                                 "move of the blobs into the dense ordered slab"},
         }
         if world == 1 and not a.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)          # the reference gets every host core again

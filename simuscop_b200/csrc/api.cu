@@ -75,7 +75,9 @@ struct ssc_handle {
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
 	bool prefetchWindows = true;  // the ticket prologue of the fast kernel prefetches its pairs' haplotype windows into the L2
-	bool carryPass2 = true;       // pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 (off: stand-alone kernel per batch)
+	bool carryPass2 = false;      // on: pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 instead of a stand-alone
+	                              // kernel per batch.  Measured neutral on the 3 Gb job: a warp of the generation kernel
+	                              // moves its 21 KB at the latency-bound rate of one warp, which costs what the stand-alone kernel costs
 	bool gzip = false;            // slabs hold gzip members (one per ticket blob) instead of plain FASTQ
 	bool haveGz = false;          // Huffman / CRC tables of the current plan are on the device
 	ssc::GzTables* d_gzTab = nullptr;

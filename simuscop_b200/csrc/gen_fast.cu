@@ -791,6 +791,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	const uint32_t* winPtr = lane < 16 ? P.hap2 + lane : P.hapN + (lane - 16);
 	const int winHalf = lane < 16 ? 0 : 1;            // a mask word covers 32 bases, a data word 16
 
+	uint32_t nmKey = 0xffffffffu, nm0 = 0, nm1 = 0;    // record-name cache of the warp (see the header code of the pair loop)
 	while (true) {
 		// ---- a ticket = FG_CHUNK consecutive pairs
 		int chunk = 0;
@@ -912,31 +913,34 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			const int nameLen = (int)((nameNd >> 17) & 127u), nameOff = (int)(nameNd & 0x1ffffu);
 			const int H = nameLen + nd1 + 1 + nd2 + (t.paired ? 2 : 0) + 1;
 			const int hWords = (H + 31) >> 5;
+			// "@<popu>#<chr>#" is the same for every pair of a segment: its characters (at most 64, two per lane) stay in
+			// registers and are fetched again only when the name changes
+			if ((nameNd & 0xffffffu) != nmKey) {
+				nmKey = nameNd & 0xffffffu;
+				nm0 = lane < nameLen ? (uint32_t)(uint8_t)P.names[nameOff + lane] : 0u;
+				nm1 = lane + 32 < nameLen ? (uint32_t)(uint8_t)P.names[nameOff + 32 + lane] : 0u;
+			}
+			const uint32_t slash = t.paired ? (uint32_t)'/' : (uint32_t)'\n';
+			const int mateAt = t.paired ? H - 2 : -1;
 #pragma unroll
 			for (int r = 0; r < 3; r++) {
 				if (r >= hWords) break;
+				// character i of the header: name | digits of pos % segsize (most significant first) | '#' | digits of the
+				// fragment counter | "/1\n" or "\n" -- selected without branches; the digits come from lanes 0..19 by shuffle
 				const int i = lane + 32 * r;
-				uint32_t ch = '\n';
-				int srcLane = 0;
-				if (i < nameLen) ch = (uint8_t)P.names[nameOff + i];
-				else {
-					const int k = i - nameLen;
-					if (k < nd1) { srcLane = nd1 - 1 - k; ch = 0; }
-					else if (k == nd1) ch = '#';
-					else {
-						const int k2 = k - nd1 - 1;
-						if (k2 < nd2) { srcLane = 10 + nd2 - 1 - k2; ch = 0; }
-						else if (t.paired && k2 == nd2) ch = '/';
-					}
-				}
-				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane);
+				const int k = i - nameLen, k2 = k - nd1 - 1;
+				const bool d1 = (unsigned)k < (unsigned)nd1, d2 = (unsigned)k2 < (unsigned)nd2;
+				const int srcLane = d1 ? nd1 - 1 - k : 9 + nd2 - k2;
+				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane & 31);
+				uint32_t ch = k == nd1 ? (uint32_t)'#' : (k2 == nd2 ? slash : (uint32_t)'\n');
+				ch = (d1 || d2) ? dv : ch;
+				if (r < 2) ch = k < 0 ? (r == 0 ? nm0 : nm1) : ch;
 				// straight into both records of the pair (the cursors of file 1 / file 2 are posA / posB here); only the mate
 				// digit in front of the final '\n' differs
 				if (i < H) {
-					const uint32_t hc = ch ? ch : dv;
-					const bool mateDigit = t.paired && i == H - 2;
-					P.out1[posA + i] = (uint8_t)(mateDigit ? '1' : hc);
-					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? '2' : hc);
+					const bool mateDigit = i == mateAt;
+					P.out1[posA + i] = (uint8_t)(mateDigit ? (uint32_t)'1' : ch);
+					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? (uint32_t)'2' : ch);
 				}
 			}
 

@@ -515,10 +515,24 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 				}
 			}
 			const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+			std::vector<std::vector<double>> drawn(101);
 			std::atomic<int> next(0);
 			auto run = [&]() {
-				for (int g = next.fetch_add(1); g <= 100; g = next.fetch_add(1))
-					for (uint32_t i : byGc[g]) factors[i] = prof.gc_factor(g);
+				for (int g = next.fetch_add(1); g <= 100; g = next.fetch_add(1)) {
+					if (byGc[g].empty()) continue;
+					// engine and distribution of this percentage on the thread's own stack while it draws: the 101 engines
+					// are 8 bytes apart in memory, neighbouring percentages would fight over the same cache line
+					std::default_random_engine eng = prof.gcEng[g];
+					std::normal_distribution<double> dist = prof.gcDist[g];
+					std::vector<double>& out = drawn[g];
+					out.resize(byGc[g].size());
+					for (size_t k = 0; k < out.size(); k++) {
+						double v = dist(eng);
+						while (v < 0) v = dist(eng);                     // Profile::getGCFactor, Profile.cpp:1507-1517
+						out[k] = v;
+					}
+					prof.gcEng[g] = eng; prof.gcDist[g] = dist;
+				}
 			};
 			if (flat < 20000 || T == 1) run();
 			else {
@@ -527,6 +541,8 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 				run();
 				for (auto& t : th) t.join();
 			}
+			for (int g = 0; g <= 100; g++)
+				for (size_t k = 0; k < drawn[g].size(); k++) factors[byGc[g][k]] = drawn[g][k];
 		}
 		for (size_t k = 0; k < v.size(); k++) {
 			if (v[k].weighted) continue;
