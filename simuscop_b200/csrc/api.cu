@@ -74,6 +74,7 @@ struct ssc_handle {
 	bool forceGeneric = false;
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
+	bool noQ16 = false;           // "no_q16": keep profiles with 9..40 live quality symbols on the diagonal-rows mode (A/B, tests)
 	bool prefetchWindows = true;  // the ticket prologue of the fast kernel prefetches its pairs' haplotype windows into the L2
 	bool carryPass2 = false;      // on: pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 instead of a stand-alone
 	                              // kernel per batch.  Measured neutral on the 3 Gb job: a warp of the generation kernel
@@ -289,7 +290,7 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 	P.bins = h->d_bins.p; P.emitBase = h->d_emitBase.p; P.nBins = h->nDevBins;
 	P.riskyAttempt = h->d_risky.p; P.names = h->d_names.p;
 	P.seed = h->seed; P.emitLo = emitLo; P.emitHi = emitHi; P.one = 1; P.noSplice = h->noSplice ? 1 : 0;
-	P.qstride = (fast && qsmem == 8) ? (uint32_t)h->dt.qualBins * 68u : 68u;   // F_QROW of gen_fast.cu
+	P.qstride = (fast && qsmem == 8) ? (uint32_t)h->dt.qualBins * 68u : 68u;   // F_QROW of gen_fast.cu (unused by the 16-bit-key mode)
 	P.insLim = h->dt.insEnable ? h->dt.insT + 1u : 0u;
 	P.delLim = h->dt.delEnable ? h->dt.delT + 1u : 0u;
 	P.alwaysSlow = (h->dt.insEnable && h->dt.insT == 0xFFFFFFFFu) || (h->dt.delEnable && h->dt.delT == 0xFFFFFFFFu);
@@ -489,6 +490,11 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
 	if (!strcmp(key, "carry_pass2")) { h->carryPass2 = value != 0; return SSC_OK; }
 	if (!strcmp(key, "prefetch_windows")) { h->prefetchWindows = value != 0; return SSC_OK; }
+	if (!strcmp(key, "no_q16")) {
+		if (h->haveProfile) return fail(SSC_ERR_STATE, "no_q16 must be set before ssc_set_profile");
+		h->noQ16 = value != 0;
+		return SSC_OK;
+	}
 	if (!strcmp(key, "max_ctas")) { if (value < 0) return fail(SSC_ERR_INVALID, "max_ctas must be >= 0"); h->maxCtas = (int)value; return SSC_OK; }
 	if (!strcmp(key, "no_splice")) { h->noSplice = value != 0; return SSC_OK; }
 	if (!strcmp(key, "force_generic")) { h->forceGeneric = value != 0; h->slabPairs = 0; return SSC_OK; }
@@ -542,6 +548,7 @@ int ssc_set_profile(ssc_handle* h, const ssc_profile_tables* t) {
 	d.delLenT = h->d_delT.p; d.delLenSym = h->d_delSym.p;
 	d.sub = h->d_sub.p; d.nSub = th.nRows * th.B;
 	d.qualT = h->d_qualT.p; d.qualSym = h->d_qualSym.p; d.qualPitch = th.qualPitch; d.nQualRows = 16 * th.B;
+	d.maxQualRow = th.maxQualRow; d.noQ16 = h->noQ16 ? 1 : 0;
 	d.qualBins = ssc::fast_choose_qbins(th.B, th.RL);
 	d.qualDiagT = h->d_qualDiagT.p; d.qualDiagSym = h->d_qualDiagSym.p; d.qualDiagPitch = th.diagPitch;
 	d.compLut = th.compLut;

@@ -37,6 +37,8 @@ struct DevTables {
 	const uint32_t* delLenT; const uint16_t* delLenSym;
 	const uint4* sub; int nSub;              // rows*B per read table; table of read 2 follows when useCdf2
 	const uint32_t* qualT; const uint8_t* qualSym; int qualPitch; int nQualRows;
+	int maxQualRow;                          // live symbols of the longest quality row
+	int noQ16;                               // tests / experiments: do not use the 16-bit-key shared-memory tables
 	int qualBins;                            // fast kernel: bins per (ref, call) block of the shared quality image (>= B, see fast_choose_qbins)
 	const uint32_t* qualDiagT; const uint8_t* qualDiagSym; int qualDiagPitch;   // ref == call rows, [N*B][pitch]
 	uint32_t compLut;

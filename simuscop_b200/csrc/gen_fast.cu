@@ -49,6 +49,8 @@ static constexpr int F_INS_CAP = 128;
 static constexpr int F_WIN_WORDS = 32;          // 16 data words + 9 mask words (+pad)
 static constexpr int F_QROW = 68;               // bytes of a shared-memory quality row (QP == 8): 8 x {threshold, sym | char << 8} + one pad
                                                 // word: an odd word pitch spreads the rows of a warp over all 32 banks
+static constexpr int F_Q16_KEYS = 40;           // QP == 16: thresholds per quality row (16-bit keys)
+static constexpr int F_Q16_ROW = 124;           // bytes of such a row: 40 keys + 40 symbols + pad (31 words: an odd word pitch)
 __host__ __device__ inline int fast_sub_pitch(int B) { return B | 1; }   // entries per substitution row, odd for the same reason
 static constexpr int F_LUT_N = 6 * 64;          // context LUT (16-bit entries: 64 entries = 32 banks, conflict free):
                                                 // fwd, rev, fwd cycle 0, fwd cycle 1, rev cycle 0, rev cycle 1
@@ -58,10 +60,10 @@ struct FastLayout {
 	int w_ev, w_insb, w_insp, w_out, w_win, perWarp;
 };
 
-__host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
+__host__ __device__ inline FastLayout fast_layout(int subBytes, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
 	FastLayout L;
 	int o = 0;
-	L.sub = o; o += nSubEntries * 16;
+	L.sub = o; o += (subBytes + 15) / 16 * 16;
 	L.qual = o; o += (qualBytes + 15) / 16 * 16;
 	L.qualSym = o; o += (qualSymBytes + 15) / 16 * 16;
 	L.isizeT = o; o += (nIsize * 4 + 15) / 16 * 16;
@@ -86,6 +88,7 @@ __host__ __device__ inline FastLayout fast_layout(int nSubEntries, int qualBytes
 
 __host__ __device__ inline void fast_qual_bytes(const DevTables& t, int qp, int* qualBytes, int* qualSymBytes) {
 	if (qp == 8) { *qualBytes = 16 * t.qualBins * F_QROW; *qualSymBytes = 0; }
+	else if (qp == 16) { *qualBytes = 16 * t.B * F_Q16_ROW; *qualSymBytes = 0; }
 	else if (qp == 2) { *qualBytes = 4 * t.B * (t.qualDiagPitch + 1) * 4; *qualSymBytes = 4 * t.B * (t.qualDiagPitch + 1); }   // odd word pitch
 	else { *qualBytes = 0; *qualSymBytes = 0; }
 }
@@ -167,6 +170,8 @@ struct WarpCtx {
 	uint32_t* insp; uint32_t* outw;   // packed inserted bases / spliced read (word 0 of each array, a pad word lies in front)
 	const uint32_t* rk;        // Philox round keys
 	uint32_t c0, c1;           // pair counter words
+	uint32_t sub16S;           // QP == 16: shared address of the 8-byte substitution entries of the current mate
+	const uint4* gsub;         // QP == 16: the exact substitution rows of the current mate in global memory (tie fallback)
 	uint32_t qualBaseS;        // shared address folded into word 3 of the substitution rows
 	uint32_t qstride;          // bytes between the quality rows (ref, call) and (ref, call + 1) of one bin
 	int lane;
@@ -203,6 +208,48 @@ __device__ __forceinline__ uint32_t qual_lookup(const QualTabs& q, uint32_t cur,
 	int k = 0;
 	for (int s = q.pitch >> 1; s > 0; s >>= 1) if (qt[k + s - 1] < u3) k += s;
 	return q.gSym[qrow * q.pitch + k];
+}
+
+// QP == 16: profiles whose quality rows have up to 40 live symbols (GAIIx, HiSeq2000, HiSeq2500).  Their 32-bit tables do not
+// fit into shared memory, their HIGH HALVES do: substitution entries {k0, k1, k2, ref*4+base} and quality rows of 40 keys +
+// 40 symbols, 16 bits per key.  For a draw u with high half uh, "u > T" is decided by "uh > key" unless uh == key (probability
+// 2^-16 per compare); a lane that meets such a tie repeats the lookup on the exact 32-bit tables in global memory.  Same
+// decision as the full compare for every u, by construction.  rowIdx: entry index of the substitution row (from the context
+// LUT), passThrough: unknown k-mer context, the base passes through (Profile.cpp:1531-1533); cur: template base (0..3).
+__device__ __forceinline__ void lookup16(const WarpCtx& w, uint32_t rowIdx, uint32_t binIdx, uint32_t u2, uint32_t u3, bool passThrough,
+                                         uint32_t cur, uint32_t& ch, uint32_t& q) {
+	uint32_t lo, hi;
+	asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(w.sub16S + (rowIdx + binIdx) * 8u));
+	const uint32_t uh2 = u2 >> 16, uh3 = u3 >> 16;
+	const uint32_t k0 = lo & 0xffffu, k1 = lo >> 16, k2 = hi & 0xffffu;
+	uint32_t rc = hi >> 16;                                         // (ref, base) row: ref * 4 + base
+	rc += (uh2 > k0) + (uh2 > k1) + (uh2 > k2);
+	bool tie = (uh2 == k0) | (uh2 == k1) | (uh2 == k2);
+	if (passThrough) { rc = cur * 5u; tie = false; }
+	const uint32_t qa = w.qualBaseS + (rc * (uint32_t)w.B + binIdx) * (uint32_t)F_Q16_ROW;
+	uint32_t k = 0;                                                 // byte offset of the first key >= uh3: lower bound over 40 keys
+	add_lt(k, lds_u16(qa + k + 38), uh3, 40u);                      // steps of 20, 10, 5, 2, 1, 1 keys
+	add_lt(k, lds_u16(qa + k + 18), uh3, 20u);
+	add_lt(k, lds_u16(qa + k + 8), uh3, 10u);
+	add_lt(k, lds_u16(qa + k + 2), uh3, 4u);
+	add_lt(k, lds_u16(qa + k), uh3, 2u);
+	add_lt(k, lds_u16(qa + k), uh3, 2u);
+	tie |= lds_u16(qa + k) == uh3;                                  // (k <= 78: the last key of a row is read at most)
+	q = lds_u8(qa + 2u * F_Q16_KEYS + (k >> 1));
+	uint32_t call = rc & 3u;
+	if (tie) {
+		// exact repeat on the 32-bit tables (global memory, L2)
+		const uint32_t row = rowIdx / (uint32_t)w.subPitch;
+		const uint4 sr = w.gsub[row * (uint32_t)w.B + binIdx];
+		call = passThrough ? cur : sr.w + (u2 > sr.x) + (u2 > sr.y) + (u2 > sr.z);
+		const uint32_t ref = passThrough ? cur : (row & 3u);
+		const uint32_t qrow = (ref * 4u + call) * (uint32_t)w.B + binIdx;
+		const uint32_t* qt = w.q.gT + qrow * w.q.pitch;
+		int kk = 0;
+		for (int st = w.q.pitch >> 1; st > 0; st >>= 1) if (qt[kk + st - 1] < u3) kk += st;
+		q = w.q.gSym[qrow * w.q.pitch + kk];
+	}
+	ch = __byte_perm(w.baseChars, 0, 0x4440u | call);
 }
 
 // template base code (0..3, 4 = non-ACGT) of read position j, from the shared window
@@ -385,10 +432,16 @@ __device__ __forceinline__ void emit_packed(const WarpCtx& w, const uint32_t* wi
 		const uint32_t v6 = __funnelshift_r(win[rel >> 4], win[(rel >> 4) + 1], (uint32_t)(rel & 15) * 2u) & 63u;
 		const uint32_t rowIdx = *(const uint16_t*)(w.lutB + (c == 0 ? lut0 : lutN) + v6 * 2u);
 		const uint32_t binIdx = __umulhi((uint32_t)(jc * w.B), inv);
+		uint32_t ch, q;
+		if (QP == 16) {
+			lookup16(w, rowIdx, binIdx, u2, u3, false, 0u, ch, q);
+			if (j < m) { *pB = (uint8_t)ch; *pQ = (uint8_t)q; }
+			pB += 32; pQ += 32;
+			continue;
+		}
 		const uint4 sr = w.sub[rowIdx + binIdx];
 		uint32_t acc = sr.w;
 		add_gt(acc, u2, sr.x, w.qstride); add_gt(acc, u2, sr.y, w.qstride); add_gt(acc, u2, sr.z, w.qstride);
-		uint32_t ch, q;
 		if (QP == 8) {
 			uint32_t qa = binIdx * (uint32_t)F_QROW + acc;
 			add_lt(qa, lds_u32(qa + 24), u3, 32u);
@@ -471,11 +524,18 @@ __device__ __forceinline__ void emit_mapped(const WarpCtx& w, const IndelPlan& p
 			const uint32_t var = j >= 2 ? 0u : (j == 0 ? 2u : 3u);                          // 'X' padded contexts
 			const uint32_t rowIdx = *(const uint16_t*)(w.lutB + var * 128u + v6 * 2u);
 			const uint32_t binIdx = __umulhi((uint32_t)(j * w.B), inv);
+			uint32_t ch, q;
+			if (QP == 16) {
+				if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
+				else lookup16(w, rowIdx, binIdx, u2, u3, n3 != 0u, cur, ch, q);
+				stB[c * 32] = (uint8_t)ch;
+				stB[m + 3 + c * 32] = (uint8_t)q;
+				continue;
+			}
 			const uint4 sr = w.sub[rowIdx + binIdx];
 			uint32_t acc = sr.w;
 			add_gt(acc, u2, sr.x, w.qstride); add_gt(acc, u2, sr.y, w.qstride); add_gt(acc, u2, sr.z, w.qstride);
 			if (n3) acc = w.qualBaseS + cur * (5u * w.qstride);                    // unknown context: the base passes through
-			uint32_t ch, q;
 			if (n3 & 4u) { ch = 'N'; q = (uint32_t)w.minQ + __umulhi(20u, u3); }   // randomInteger(33, 53), Profile.cpp:1583
 			else if (QP == 8) {
 				uint32_t qa = binIdx * (uint32_t)F_QROW + acc;
@@ -672,7 +732,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	fast_qual_bytes(t, QP, &qualBytes, &qualSymBytes);
 	const int subPitch = fast_sub_pitch(t.B);
 	const int nRowsTotal = nSubTotal / t.B;
-	const FastLayout L = fast_layout(nRowsTotal * subPitch, qualBytes, qualSymBytes, t.nIsize, t.nInsLen, t.nDelLen);
+	const FastLayout L = fast_layout(nRowsTotal * subPitch * (QP == 16 ? 8 : 16), qualBytes, qualSymBytes, t.nIsize, t.nInsLen, t.nDelLen);
 
 	uint4* s_sub = (uint4*)(smem + L.sub);
 	uint8_t* s_qual = smem + L.qual;
@@ -688,7 +748,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 	const int RL = t.RL, B = t.B;
 	// shared-window address of the quality rows, folded into the substitution rows (QP == 8)
-	const uint32_t qualBaseS = QP == 8 ? (uint32_t)__cvta_generic_to_shared(s_qual) : 0u;
+	const uint32_t qualBaseS = (QP == 8 || QP == 16) ? (uint32_t)__cvta_generic_to_shared(s_qual) : 0u;
 	const uint32_t qstride = P.qstride;            // QP == 8: qualBins * F_QROW, else F_QROW
 	// ---- stage the tables
 	// substitution rows: word 3 becomes the byte offset of the quality row (ref, base) inside a bin block;
@@ -698,10 +758,25 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 		uint4 v = t.sub[i];
 		const int rowAll = i / B, bin = i - rowAll * B;
 		const int row = rowAll % t.nRows;
-		v.w = qualBaseS + ((uint32_t)(row & 3) * 4u + v.w) * qstride;
-		s_sub[rowAll * subPitch + bin] = v;
+		if (QP == 16) {
+			// high halves of the three thresholds + the (ref, base) row
+			((uint2*)s_sub)[rowAll * subPitch + bin] = make_uint2((v.x >> 16) | (v.y & 0xffff0000u), (v.z >> 16) | (((uint32_t)(row & 3) * 4u + v.w) << 16));
+		} else {
+			v.w = qualBaseS + ((uint32_t)(row & 3) * 4u + v.w) * qstride;
+			s_sub[rowAll * subPitch + bin] = v;
+		}
 	}
-	if (QP == 8) {
+	if (QP == 16) {
+		// [ref*4+call][bin] rows of 40 keys (high halves of the thresholds; rows are padded with 0xFFFFFFFF) + 40 symbols
+#pragma unroll 1
+		for (int i = threadIdx.x; i < t.nQualRows * F_Q16_KEYS; i += FG_THREADS) {
+			const int r = i / F_Q16_KEYS, k = i - r * F_Q16_KEYS;
+			const int src = r * t.qualPitch + (k < t.qualPitch ? k : t.qualPitch - 1);
+			uint8_t* row = s_qual + r * F_Q16_ROW;
+			((uint16_t*)row)[k] = k < t.qualPitch ? (uint16_t)(t.qualT[src] >> 16) : (uint16_t)0xffffu;
+			row[2 * F_Q16_KEYS + k] = t.qualSym[src];
+		}
+	} else if (QP == 8) {
 		// [ref*4+call][bin][8] x {threshold, sym | char << 8}: the rows one warp instruction touches (about eleven bins x
 		// four ref == call rows) spread over the banks; t.qualBins >= B pads the (ref, call) blocks for that
 #pragma unroll 1
@@ -791,7 +866,6 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 	const uint32_t* winPtr = lane < 16 ? P.hap2 + lane : P.hapN + (lane - 16);
 	const int winHalf = lane < 16 ? 0 : 1;            // a mask word covers 32 bases, a data word 16
 
-	uint32_t nmKey = 0xffffffffu, nm0 = 0, nm1 = 0;    // record-name cache of the warp (see the header code of the pair loop)
 	while (true) {
 		// ---- a ticket = FG_CHUNK consecutive pairs
 		int chunk = 0;
@@ -913,34 +987,31 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			const int nameLen = (int)((nameNd >> 17) & 127u), nameOff = (int)(nameNd & 0x1ffffu);
 			const int H = nameLen + nd1 + 1 + nd2 + (t.paired ? 2 : 0) + 1;
 			const int hWords = (H + 31) >> 5;
-			// "@<popu>#<chr>#" is the same for every pair of a segment: its characters (at most 64, two per lane) stay in
-			// registers and are fetched again only when the name changes
-			if ((nameNd & 0xffffffu) != nmKey) {
-				nmKey = nameNd & 0xffffffu;
-				nm0 = lane < nameLen ? (uint32_t)(uint8_t)P.names[nameOff + lane] : 0u;
-				nm1 = lane + 32 < nameLen ? (uint32_t)(uint8_t)P.names[nameOff + 32 + lane] : 0u;
-			}
-			const uint32_t slash = t.paired ? (uint32_t)'/' : (uint32_t)'\n';
-			const int mateAt = t.paired ? H - 2 : -1;
 #pragma unroll
 			for (int r = 0; r < 3; r++) {
 				if (r >= hWords) break;
-				// character i of the header: name | digits of pos % segsize (most significant first) | '#' | digits of the
-				// fragment counter | "/1\n" or "\n" -- selected without branches; the digits come from lanes 0..19 by shuffle
 				const int i = lane + 32 * r;
-				const int k = i - nameLen, k2 = k - nd1 - 1;
-				const bool d1 = (unsigned)k < (unsigned)nd1, d2 = (unsigned)k2 < (unsigned)nd2;
-				const int srcLane = d1 ? nd1 - 1 - k : 9 + nd2 - k2;
-				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane & 31);
-				uint32_t ch = k == nd1 ? (uint32_t)'#' : (k2 == nd2 ? slash : (uint32_t)'\n');
-				ch = (d1 || d2) ? dv : ch;
-				if (r < 2) ch = k < 0 ? (r == 0 ? nm0 : nm1) : ch;
+				uint32_t ch = '\n';
+				int srcLane = 0;
+				if (i < nameLen) ch = (uint8_t)P.names[nameOff + i];
+				else {
+					const int k = i - nameLen;
+					if (k < nd1) { srcLane = nd1 - 1 - k; ch = 0; }
+					else if (k == nd1) ch = '#';
+					else {
+						const int k2 = k - nd1 - 1;
+						if (k2 < nd2) { srcLane = 10 + nd2 - 1 - k2; ch = 0; }
+						else if (t.paired && k2 == nd2) ch = '/';
+					}
+				}
+				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane);
 				// straight into both records of the pair (the cursors of file 1 / file 2 are posA / posB here); only the mate
 				// digit in front of the final '\n' differs
 				if (i < H) {
-					const bool mateDigit = i == mateAt;
-					P.out1[posA + i] = (uint8_t)(mateDigit ? (uint32_t)'1' : ch);
-					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? (uint32_t)'2' : ch);
+					const uint32_t hc = ch ? ch : dv;
+					const bool mateDigit = t.paired && i == H - 2;
+					P.out1[posA + i] = (uint8_t)(mateDigit ? '1' : hc);
+					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? '2' : hc);
 				}
 			}
 
@@ -957,6 +1028,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 				uint8_t* stage = P.out1 + posA;
 				const uint4* subM = s_sub + ((mate == 1 && t.useCdf2) ? t.nRows * subPitch : 0);
 				w.sub = subM;
+				if (QP == 16) {
+					w.sub16S = (uint32_t)__cvta_generic_to_shared(s_sub) + ((mate == 1 && t.useCdf2) ? (uint32_t)(t.nRows * subPitch) * 8u : 0u);
+					w.gsub = t.sub + ((mate == 1 && t.useCdf2) ? t.nSub : 0);
+				}
 
 				// ---- phase A: one Philox block per cycle (chunks interleaved); indel candidates at reference position j
 				uint32_t x0[NCH], x1[NCH], x2[NCH], x3[NCH];
@@ -988,13 +1063,19 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 					for (int c = 0; c < NCH; c++) {
 						const uint32_t v6 = __funnelshift_r(dptr[c * dstep], dptr[c * dstep + 1], dsh) & 63u;
 						const uint32_t rowIdx = *(const uint16_t*)((c == 0 ? lut0 : lutN) + v6 * 2u);
-						const uint4 sr = *(const uint4*)(subMB + (rowIdx + binOf[c]) * 16u);
-						uint32_t acc = sr.w;
-						fadd_gt(acc, x2[c], sr.x, P.qstride, one);
-						fadd_gt(acc, x2[c], sr.y, P.qstride, one);
-						fadd_gt(acc, x2[c], sr.z, P.qstride, one);
 						uint32_t ch, q;
-						if (QP == 8) {
+						uint4 sr = make_uint4(0u, 0u, 0u, 0u);
+						uint32_t acc = 0;
+						if (QP == 16) lookup16(w, rowIdx, binOf[c], x2[c], x3[c], false, 0u, ch, q);
+						else {
+							sr = *(const uint4*)(subMB + (rowIdx + binOf[c]) * 16u);
+							acc = sr.w;
+							fadd_gt(acc, x2[c], sr.x, P.qstride, one);
+							fadd_gt(acc, x2[c], sr.y, P.qstride, one);
+							fadd_gt(acc, x2[c], sr.z, P.qstride, one);
+						}
+						if (QP == 16) {
+						} else if (QP == 8) {
 							uint32_t qa = binOf[c] * (uint32_t)F_QROW + acc;         // shared address of row (ref, call, bin)
 							fadd_lt(qa, lds_u32(qa + 24), x3[c], 32u, one);
 							fadd_lt(qa, lds_u32(qa + 8), x3[c], 16u, one);
@@ -1105,12 +1186,15 @@ int fast_choose_qbins(int B, int RL) {
 bool fast_supported(const DevTables& t, int smemLimit, int* qmode, size_t* smemBytes) {
 	if (t.N != 4 || t.K != 3 || t.RL > 160 || t.RL < 33 || t.nIsize > 1024 || t.B > 160) return false;
 	const int nSubTotal = t.nSub * (t.useCdf2 ? 2 : 1);
-	const int modes[3] = {8, 2, 0};
-	for (int k = 0; k < 3; k++) {
+	// 8: all quality rows (<= 8 live symbols) in shared memory, 32-bit; 16: all rows (<= 40 live symbols) with 16-bit keys;
+	// 2: only the ref == call rows; 0: quality table in global memory
+	const int modes[4] = {8, 16, 2, 0};
+	for (int k = 0; k < 4; k++) {
 		if (modes[k] == 8 && t.qualPitch != 8) continue;
+		if (modes[k] == 16 && (t.maxQualRow > F_Q16_KEYS || t.noQ16)) continue;
 		int qb, qs;
 		fast_qual_bytes(t, modes[k], &qb, &qs);
-		const int total = fast_layout(nSubTotal / t.B * fast_sub_pitch(t.B), qb, qs, t.nIsize, t.nInsLen, t.nDelLen).total;
+		const int total = fast_layout(nSubTotal / t.B * fast_sub_pitch(t.B) * (modes[k] == 16 ? 8 : 16), qb, qs, t.nIsize, t.nInsLen, t.nDelLen).total;
 		if (total <= smemLimit) { *qmode = modes[k]; *smemBytes = (size_t)total; return true; }
 	}
 	return false;
@@ -1137,6 +1221,11 @@ cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes
 		else if (nch == 3) e = launch_fast_variant<3, 8>(P, smemBytes, grid, stream);
 		else if (nch == 4) e = launch_fast_variant<4, 8>(P, smemBytes, grid, stream);
 		else e = launch_fast_variant<5, 8>(P, smemBytes, grid, stream);
+	} else if (qmode == 16) {
+		if (nch <= 2) e = launch_fast_variant<2, 16>(P, smemBytes, grid, stream);
+		else if (nch == 3) e = launch_fast_variant<3, 16>(P, smemBytes, grid, stream);
+		else if (nch == 4) e = launch_fast_variant<4, 16>(P, smemBytes, grid, stream);
+		else e = launch_fast_variant<5, 16>(P, smemBytes, grid, stream);
 	} else if (qmode == 2) {
 		if (nch <= 2) e = launch_fast_variant<2, 2>(P, smemBytes, grid, stream);
 		else if (nch == 3) e = launch_fast_variant<3, 2>(P, smemBytes, grid, stream);
