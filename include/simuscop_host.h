@@ -35,6 +35,11 @@ const char* ssh_output_dir(ssh_job* job);
 /* dump_path may be NULL; otherwise an SSCPLAN1 file of the sample is written there */
 int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_path,
                        int64_t* planned_pairs, int64_t* emitted_pairs);
+/* Host-only self test (no GPU): the splice lists from which the device assembles haplotypes with insertion / deletion
+ * variants, materialised on the host, against the string construction of Segment::generateSegSequences
+ * (lib/segment/Segment.cpp:124-460).  Returns the number of differing haplotypes. */
+int ssh_selftest_splices(ssh_job* job, int64_t* haplotypes_checked, int64_t* segments_with_indels);
+
 /* Output side (the role of SeqWriter, lib/seqwriter/SeqWriter.cpp:41-54): an ordered FASTQ file writer whose sink can be
  * handed to ssc_generate with user = the writer.  path2 NULL = single-end.  Every slab is cut into chunks that `threads`
  * workers pwrite() at their final offsets (threads <= 1: written by the caller's thread). */

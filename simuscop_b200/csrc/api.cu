@@ -74,6 +74,10 @@ struct ssc_handle {
 	bool forceGeneric = false;
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
+	int moverCtas = 0;            // "concurrent_move" > 0: pass 2b of batch k runs on that many SMs (bulk-copy mover, second stream) under the
+	                              // generation kernel of batch k+1, which leaves them free
+	cudaStream_t mover = nullptr;
+	cudaEvent_t evPre = nullptr, evScanned[2] = {nullptr, nullptr}, evMoved[2] = {nullptr, nullptr};
 	bool noQ16 = false;           // "no_q16": keep profiles with 9..40 live quality symbols on the diagonal-rows mode (A/B, tests)
 	bool prefetchWindows = true;  // the ticket prologue of the fast kernel prefetches its pairs' haplotype windows into the L2
 	bool carryPass2 = false;      // on: pass 2b (blob moves) of batch k rides on the generation kernel of batch k+1 instead of a stand-alone
@@ -107,6 +111,10 @@ struct ssc_handle {
 	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
 	uint8_t* d_stage[2] = {nullptr, nullptr};
 	cudaEvent_t evStage[2] = {nullptr, nullptr};
+	static constexpr int FA_READERS = 4;          // ssc_reference_upload_fasta: reader threads, one pinned buffer each
+	uint8_t* h_fa[FA_READERS] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t evFa[FA_READERS] = {nullptr, nullptr, nullptr, nullptr};
+	size_t faBytes = 16u << 20;
 	size_t stageBytes = 32u << 20;
 
 	// plan
@@ -318,7 +326,20 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 			h->kevUsed += 3;
 		}
 		if (!h->gzip) {
-			if (h->pending.valid) {
+			int movedBuf = -1;
+			if (h->pending.valid && h->moverCtas > 0 && h->moverCtas < h->smCount) {
+				// pass 2b of the previous batch on the mover stream, under this batch's generation kernel (which leaves it the SMs)
+				const ssc::GenParams& Q = h->pending.P;
+				movedBuf = buf ^ 1;
+				CK(cudaEventRecord(h->evPre, s));                          // everything this launch had to wait for (copies, ...)
+				CK(cudaStreamWaitEvent(h->mover, h->evPre, 0));
+				CK(cudaStreamWaitEvent(h->mover, h->evScanned[movedBuf], 0));
+				CK(ssc::launch_move_blobs_tma(Q, h->moverCtas, h->mover));
+				CK(cudaEventRecord(h->evMoved[movedBuf], h->mover));
+				h->pending.valid = false;
+				h->stats.launches += 1;
+			}
+			if (h->pending.valid && h->carryPass2) {
 				// this launch carries pass 2b of the previous batch
 				const ssc::GenParams& Q = h->pending.P;
 				P.nTilesPrev = Q.nTiles; P.nLoop = std::max(nTiles, Q.nTiles);
@@ -327,14 +348,18 @@ int launch_batch(ssc_handle* h, int buf, int64_t emitLo, int64_t emitHi) {
 				P.prevDense1 = Q.dense1; P.prevDense2 = Q.dense2; P.prevCap1 = Q.cap1; P.prevCap2 = Q.cap2;
 				h->pending.valid = false;
 			}
-			grid = std::min((P.nLoop + FG_GEN - 1) / FG_GEN, h->smCount);
+			if (h->pending.valid) { int rc = flush_pending(h); if (rc) return rc; }     // (neither carried nor moved concurrently)
+			grid = std::min((P.nLoop + FG_GEN - 1) / FG_GEN, h->smCount - (movedBuf >= 0 ? h->moverCtas : 0));
 			if (h->maxCtas > 0) grid = std::min(grid, h->maxCtas);
 			CK(ssc::launch_generate_fast(P, qsmem, fastSmem, grid, s, e0, e1));
 			CK(ssc::launch_scan_blobs(P, s));
+			CK(cudaEventRecord(h->evScanned[buf], s));
 			h->pending.P = P; h->pending.valid = true;
 			h->stats.launches += 2;
-			if (!h->carryPass2) { int rc = flush_pending(h); if (rc) return rc; }
+			if (!h->carryPass2 && h->moverCtas <= 0) { int rc = flush_pending(h); if (rc) return rc; }
 			if (e2) CK(cudaEventRecord(e2, s));
+			// later work on this stream (the next launch reuses the blob scratch, copies read the dense slab) comes after the mover
+			if (movedBuf >= 0) CK(cudaStreamWaitEvent(s, h->evMoved[movedBuf], 0));
 		} else {
 			// gzip mode: blobs -> (first batch of a plan: fit the Huffman table to a sample) -> one gzip member per blob -> pass 2 on the members
 			int rc = flush_pending(h);
@@ -406,6 +431,8 @@ static int init_handle(ssc_handle* h, int device) {
 	CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&h->copy2, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->mover, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&h->evPre, cudaEventDisableTiming));
 	CK(cudaEventCreate(&h->evStart));
 	CK(cudaEventCreate(&h->evStop));
 	for (int i = 0; i < 2; i++) {
@@ -414,6 +441,8 @@ static int init_handle(ssc_handle* h, int device) {
 		CK(cudaEventCreateWithFlags(&h->evCopy2[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evStage[i], cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&h->evDense[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evScanned[i], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->evMoved[i], cudaEventDisableTiming));
 		CK(cudaMalloc((void**)&h->d_result[i], sizeof(ssc::BatchResult)));
 		CK(cudaMallocHost((void**)&h->h_result[i], sizeof(ssc::BatchResult)));
 	}
@@ -448,9 +477,15 @@ int ssc_destroy(ssc_handle* h) {
 		}
 		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
 		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
+		for (int r = b; r < ssc_handle::FA_READERS; r += 2) {
+			if (h->h_fa[r]) cudaFreeHost(h->h_fa[r]);
+			if (h->evFa[r]) cudaEventDestroy(h->evFa[r]);
+		}
 		if (h->d_slots[b][0]) cudaFree(h->d_slots[b][0]);       // d_slots[b][1] points into the same allocation
 		h->d_blobPrefix[b].release();
 		if (h->evDense[b]) cudaEventDestroy(h->evDense[b]);
+		if (h->evScanned[b]) cudaEventDestroy(h->evScanned[b]);
+		if (h->evMoved[b]) cudaEventDestroy(h->evMoved[b]);
 		if (h->d_result[b]) cudaFree(h->d_result[b]);
 		if (h->h_result[b]) cudaFreeHost(h->h_result[b]);
 		h->d_tileStart[b].release(); h->d_tileState[b].release(); h->d_ticket[b].release();
@@ -476,6 +511,8 @@ int ssc_destroy(ssc_handle* h) {
 	if (h->compute) cudaStreamDestroy(h->compute);
 	if (h->copy) cudaStreamDestroy(h->copy);
 	if (h->copy2) cudaStreamDestroy(h->copy2);
+	if (h->mover) cudaStreamDestroy(h->mover);
+	if (h->evPre) cudaEventDestroy(h->evPre);
 	delete h;
 	return SSC_OK;
 }
@@ -489,6 +526,11 @@ int ssc_set_option(ssc_handle* h, const char* key, int64_t value) {
 	}
 	if (!strcmp(key, "gzip")) { h->gzip = value != 0; return SSC_OK; }
 	if (!strcmp(key, "carry_pass2")) { h->carryPass2 = value != 0; return SSC_OK; }
+	if (!strcmp(key, "concurrent_move")) {
+		if (value < 0 || value > 64) return fail(SSC_ERR_INVALID, "concurrent_move: 0 (off) .. 64 SMs");
+		h->moverCtas = (int)value;
+		return SSC_OK;
+	}
 	if (!strcmp(key, "prefetch_windows")) { h->prefetchWindows = value != 0; return SSC_OK; }
 	if (!strcmp(key, "no_q16")) {
 		if (h->haveProfile) return fail(SSC_ERR_STATE, "no_q16 must be set before ssc_set_profile");
@@ -637,42 +679,45 @@ int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint
 	if (h->d_ref.n < n_bases + 16) CK(h->d_ref.alloc((size_t)n_bases + (size_t)n_bases / 8 + 4096));
 	if (h->d_raw.n < raw_len) CK(h->d_raw.alloc((size_t)raw_len + (size_t)raw_len / 8 + 4096));
 	if (!h->d_other.p) CK(h->d_other.alloc(1));
-	for (int i = 0; i < 2; i++) {
-		if (!h->h_stage[i]) CK(cudaMallocHost((void**)&h->h_stage[i], h->stageBytes));
+	const int NR = ssc_handle::FA_READERS;
+	for (int i = 0; i < NR; i++) {
+		if (!h->h_fa[i]) CK(cudaMallocHost((void**)&h->h_fa[i], h->faBytes));
+		if (!h->evFa[i]) CK(cudaEventCreateWithFlags(&h->evFa[i], cudaEventDisableTiming));
 	}
 	cudaStream_t s = h->compute;
 	CK(cudaMemsetAsync(h->d_other.p, 0, 8, s));
-	// file -> pinned staging (pread) -> device.  Two staging buffers, each fed by its own host thread (even / odd chunks): the
-	// page-cache copy of pread is the slow part, so two of them run at a time, under the DMA of earlier chunks (and under the
-	// pack kernels of the previous chromosome that are still queued on the stream).
-	const uint64_t nChunks = (raw_len + h->stageBytes - 1) / h->stageBytes;
-	int rcs[2] = {SSC_OK, SSC_OK};
-	std::string errMsg[2];
+	// file -> pinned staging (pread) -> device.  NR staging buffers, each fed by its own host thread (chunk c goes to reader
+	// c mod NR): the page-cache copy of pread is the slow part, so several run at a time, under the DMA of earlier chunks
+	// (and under the pack kernels of the previous chromosome that are still queued on the stream).
+	const uint64_t nChunks = (raw_len + h->faBytes - 1) / h->faBytes;
+	int rcs[ssc_handle::FA_READERS] = {SSC_OK, SSC_OK, SSC_OK, SSC_OK};
+	std::string errMsg[ssc_handle::FA_READERS];
 	auto feed = [&](int k) {
 		if (cudaSetDevice(h->device) != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = "cudaSetDevice failed"; return; }
-		for (uint64_t c = (uint64_t)k; c < nChunks; c += 2) {
-			const uint64_t done = c * h->stageBytes;
-			const size_t chunk = (size_t)std::min<uint64_t>(h->stageBytes, raw_len - done);
-			cudaError_t e = cudaEventSynchronize(h->evStage[k]);          // staging buffer k free again
+		for (uint64_t c = (uint64_t)k; c < nChunks; c += NR) {
+			const uint64_t done = c * h->faBytes;
+			const size_t chunk = (size_t)std::min<uint64_t>(h->faBytes, raw_len - done);
+			cudaError_t e = cudaEventSynchronize(h->evFa[k]);             // staging buffer k free again
 			size_t got = 0;
 			while (e == cudaSuccess && got < chunk) {
-				const ssize_t r = pread(fd, h->h_stage[k] + got, chunk - got, (off_t)(file_offset + done + got));
+				const ssize_t r = pread(fd, h->h_fa[k] + got, chunk - got, (off_t)(file_offset + done + got));
 				if (r < 0) { if (errno == EINTR) continue; rcs[k] = SSC_ERR_INVALID; errMsg[k] = std::string("reading the FASTA file failed: ") + strerror(errno); return; }
 				if (r == 0) break;                                         // a last line without a line feed ends the file early
 				got += (size_t)r;
 			}
-			if (got < chunk) memset(h->h_stage[k] + got, '\n', chunk - got);
-			if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_raw.p + done, h->h_stage[k], chunk, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess) e = cudaEventRecord(h->evStage[k], s);
+			if (got < chunk) memset(h->h_fa[k] + got, '\n', chunk - got);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_raw.p + done, h->h_fa[k], chunk, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess) e = cudaEventRecord(h->evFa[k], s);
 			if (e != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = std::string("staging the FASTA record failed: ") + cudaGetErrorString(e); return; }
 		}
 	};
-	if (nChunks > 1) {
-		std::thread other(feed, 1);
+	{
+		std::vector<std::thread> readers;
+		for (int k = 1; k < NR && (uint64_t)k < nChunks; k++) readers.emplace_back(feed, k);
 		feed(0);
-		other.join();
-	} else feed(0);
-	for (int k = 0; k < 2; k++) if (rcs[k]) return fail(rcs[k], "%s", errMsg[k].c_str());
+		for (auto& t : readers) t.join();
+	}
+	for (int k = 0; k < NR; k++) if (rcs[k]) return fail(rcs[k], "%s", errMsg[k].c_str());
 	h->stats.h2d_bytes += raw_len;
 	CK(ssc::launch_unfold(h->d_raw.p, raw_len, n_bases, line_bases, line_width, h->d_ref.p, h->d_other.p, s));
 	unsigned long long other = 0;
@@ -900,40 +945,62 @@ int ssc_set_plan(ssc_handle* h, uint64_t seed, const ssc_bin* bins, int64_t n_bi
 	});
 	for (unsigned k = 0; k < T; k++) if (segErrAt[k] >= 0) return fail(SSC_ERR_INVALID, "bin %lld %s", (long long)segErrAt[k], segErr[k]);
 	for (int64_t sIdx = 0; sIdx < n_segs; sIdx++) segOff[sIdx + 1] += segOff[sIdx];
-	std::vector<ssc::DevBin> dev((size_t)segOff[n_segs]);
+	const size_t nDev = (size_t)segOff[n_segs];
 	std::vector<int64_t>& devEmitBase = h->devEmitBase;
-	devEmitBase.assign((size_t)segOff[n_segs] + 1, 0);
-	parallel(n_segs, [&](int64_t lo, int64_t hi, unsigned) {
-		for (int64_t sIdx = lo; sIdx < hi; sIdx++) {
-			int64_t fragBase = 0, o = segOff[sIdx];
-			for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
-				if (emit[i] > 0) {
-					ssc::DevBin d;
-					d.hap_base = bins[i].hap_base + SSC_GPAD; d.contig_end = bins[i].contig_end + SSC_GPAD;
-					d.plan_base = pb[i]; d.emit_base = eb[i];
-					d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
-					d.frag_base = (int32_t)fragBase;
-					d.name_off = segs[sIdx].name_offset; d.name_len = segs[sIdx].name_len;
-					d.risky_base = riskyBase[i]; d.pad = 0;
-					dev[(size_t)o] = d;
-					devEmitBase[(size_t)o] = eb[i];
-					o++;
+	devEmitBase.assign(nDev + 1, 0);
+	// The device bins (64 bytes each, 384 MB for a 3 Gb diploid plan) are formatted straight into the two pinned staging
+	// buffers, a run of whole segments at a time, and copied from there: no pageable image of the table is ever built.
+	for (int i = 0; i < 2; i++) {
+		if (!h->h_stage[i]) CK(cudaMallocHost((void**)&h->h_stage[i], h->stageBytes));
+		CK(cudaEventSynchronize(h->evStage[i]));
+	}
+	CK(h->d_bins.alloc(std::max<size_t>(nDev, 1)));
+	const size_t perChunk = h->stageBytes / sizeof(ssc::DevBin);
+	int stage = 0;
+	for (int64_t s0 = 0; s0 < n_segs;) {
+		int64_t s1 = s0;
+		while (s1 < n_segs && (size_t)(segOff[s1 + 1] - segOff[s0]) <= perChunk) s1++;
+		if (s1 == s0) return fail(SSC_ERR_INVALID, "segment %lld has more than %zu bins", (long long)s0, perChunk);
+		const int64_t o0 = segOff[s0], cnt = segOff[s1] - o0;
+		if (cnt > 0) {
+			CK(cudaEventSynchronize(h->evStage[stage]));
+			ssc::DevBin* out = (ssc::DevBin*)h->h_stage[stage];
+			parallel(s1 - s0, [&](int64_t lo, int64_t hi, unsigned) {
+				for (int64_t sIdx = s0 + lo; sIdx < s0 + hi; sIdx++) {
+					int64_t fragBase = 0, o = segOff[sIdx];
+					for (int64_t i = segs[sIdx].first_bin; i < segs[sIdx].first_bin + segs[sIdx].n_bins; i++) {
+						if (emit[i] > 0) {
+							ssc::DevBin d;
+							d.hap_base = bins[i].hap_base + SSC_GPAD; d.contig_end = bins[i].contig_end + SSC_GPAD;
+							d.plan_base = pb[i]; d.emit_base = eb[i];
+							d.spos = bins[i].spos; d.epos = bins[i].epos; d.segsize = bins[i].segsize;
+							d.frag_base = (int32_t)fragBase;
+							d.name_off = segs[sIdx].name_offset; d.name_len = segs[sIdx].name_len;
+							d.risky_base = riskyBase[i]; d.pad = 0;
+							out[o - o0] = d;
+							devEmitBase[(size_t)o] = eb[i];
+							o++;
+						}
+						fragBase += emit[i];
+					}
 				}
-				fragBase += emit[i];
-			}
+			});
+			CK(cudaMemcpyAsync(h->d_bins.p + o0, out, (size_t)cnt * sizeof(ssc::DevBin), cudaMemcpyHostToDevice, s));
+			CK(cudaEventRecord(h->evStage[stage], s));
+			stage ^= 1;
 		}
-	});
-	devEmitBase[(size_t)segOff[n_segs]] = h->emittedPairs;
+		s0 = s1;
+	}
+	devEmitBase[nDev] = h->emittedPairs;
 	for (size_t k = 1; k + 1 < devEmitBase.size(); k++)
 		if (devEmitBase[k] <= devEmitBase[k - 1]) return fail(SSC_ERR_INVALID, "segments must list their bins in increasing, non-overlapping order");
-	h->nDevBins = (int64_t)dev.size();
-	CK(h->d_bins.upload(dev, s));
+	h->nDevBins = (int64_t)nDev;
 	CK(h->d_emitBase.upload(devEmitBase, s));
 	std::vector<char> nm(names, names + names_len);
 	nm.push_back(0);
 	CK(h->d_names.upload(nm, s));
 	CK(cudaStreamSynchronize(s));
-	h->stats.h2d_bytes += dev.size() * sizeof(ssc::DevBin) + devEmitBase.size() * 8;
+	h->stats.h2d_bytes += nDev * sizeof(ssc::DevBin) + devEmitBase.size() * 8;
 	// worst-case record bytes per pair per file: header + 2*(RL + 96) + 4
 	h->maxRecBytes = maxName + 10 + 1 + 10 + 3 + 2 * (RL + 16) + 4;
 	h->havePlan = true;
@@ -960,7 +1027,7 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 	// batch k-1 (file 1 / file 2 on two streams), which run under the sink of batch k-2.  h_out[k & 1] was consumed by the
 	// sink of batch k-2 an iteration before the copy of batch k is issued.
 	int qm = 0; size_t sb = 0;
-	const bool carried = use_fast(h, &qm, &sb) && !h->gzip && h->carryPass2;     // pass 2b of batch k rides on the launch of batch k+1
+	const bool carried = use_fast(h, &qm, &sb) && !h->gzip && (h->carryPass2 || h->moverCtas > 0);     // pass 2b of batch k rides on the launch of batch k+1
 	auto launch = [&](int k) -> int {
 		// the dense slab this launch writes: d_out[(k-1) & 1] when it carries the previous batch's moves, else d_out[k & 1];
 		// its last reader is the copy of the batch two before the one that now lands there

@@ -719,6 +719,115 @@ __global__ void __launch_bounds__(CP_THREADS, 8) move_blobs_kernel(const GenPara
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 2b on a few SMs, under the generation kernel of the next batch (round 2).
+// The stand-alone move kernel reaches its 5 TB/s with ~9 500 warps in flight (each warp is bound by the latency of its own
+// loads), i.e. it needs the whole GPU -- which the generation kernel needs too.  This form needs 8 of the 148 SMs: every
+// warp pulls a blob in 4 KB pieces into its own shared-memory ring with bulk asynchronous copies (cp.async.bulk, the TMA
+// engine: no registers, no warp stalled on a load), waits on the ring's mbarriers, and stores the pieces 16 bytes per lane
+// at their final, arbitrarily aligned place (two LDS.128 + four funnel shifts per store).  A warp keeps up to 12 KB in flight
+// instead of 2.5 KB, so 128 warps move a batch in less time than the other 140 SMs need to generate the next one.
+// ---------------------------------------------------------------------------------------------
+static constexpr int MV_WARPS = 16;
+static constexpr int MV_THREADS = MV_WARPS * 32;
+static constexpr int MV_STAGES = 3;
+static constexpr int MV_PIECE = 4096;
+static constexpr int MV_STAGE_BYTES = MV_PIECE + 32;         // the vector loop reads one 16-byte chunk past the piece
+static constexpr int MV_WARP_BYTES = MV_STAGES * MV_STAGE_BYTES + 32;   // + the ring's mbarriers
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tMV_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra MV_WAIT;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dstShared, const void* src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstShared), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// one piece (n <= 4096 bytes, in the warp's stage at shared address st) to dst (any alignment)
+template <int Q0>
+__device__ __forceinline__ void store_piece_vectors(uint32_t st, uint4* __restrict__ dv, int nvec, int r8, int lane) {
+#pragma unroll 2
+	for (int v = lane; v < nvec; v += 32) {
+		uint32_t w[8];
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(st + 16u * v));
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(st + 16u * v + 16u));
+		uint4 o;
+		o.x = __funnelshift_r(w[Q0], w[Q0 + 1], r8);
+		o.y = __funnelshift_r(w[Q0 + 1], w[Q0 + 2], r8);
+		o.z = __funnelshift_r(w[Q0 + 2], w[Q0 + 3], r8);
+		o.w = __funnelshift_r(w[Q0 + 3], w[Q0 + 4], r8);
+		__stcs(dv + v, o);
+	}
+}
+
+__device__ __forceinline__ void store_piece(uint32_t st, const uint8_t* stGeneric, int n, uint8_t* __restrict__ dst, int lane) {
+	int head = (int)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+	if (head > n) head = n;
+	if (lane < head) dst[lane] = stGeneric[lane];
+	const int nvec = (n - head) >> 4;
+	const int r8 = (head & 3) * 8;
+	uint4* dv = (uint4*)(dst + head);
+	switch (head >> 2) {
+	case 0: store_piece_vectors<0>(st, dv, nvec, r8, lane); break;
+	case 1: store_piece_vectors<1>(st, dv, nvec, r8, lane); break;
+	case 2: store_piece_vectors<2>(st, dv, nvec, r8, lane); break;
+	default: store_piece_vectors<3>(st, dv, nvec, r8, lane); break;
+	}
+	const int t0 = head + (nvec << 4);
+	if (lane < n - t0) dst[t0 + lane] = stGeneric[t0 + lane];
+}
+
+__global__ void __launch_bounds__(MV_THREADS, 1) move_blobs_tma_kernel(const GenParams P) {
+	extern __shared__ __align__(128) uint8_t mv_smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint8_t* ring = mv_smem + warp * MV_WARP_BYTES;
+	const uint32_t ringS = (uint32_t)__cvta_generic_to_shared(ring);
+	const uint32_t barS = ringS + MV_STAGES * MV_STAGE_BYTES;
+	if (lane == 0) {
+		for (int i = 0; i < MV_STAGES; i++) mbar_init(barS + 8u * i, 1u);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	uint32_t phase = 0;                               // one parity bit per stage
+	const int nWarps = gridDim.x * MV_WARPS;
+	for (int j = blockIdx.x * MV_WARPS + warp; j < P.nTiles; j += nWarps) {
+		const unsigned long long excl = __ldcg(P.blobPrefix + j), mine = __ldcg(P.tileState + j);
+		const unsigned long long d[2] = {excl >> 31, excl & 0x7fffffffull};
+		const int len[2] = {(int)(mine >> 31), (int)(mine & 0x7fffffffull)};
+		if (d[0] + (unsigned)len[0] > P.cap1 || d[1] + (unsigned)len[1] > P.cap2) continue;   // flagged by the scan
+#pragma unroll 1
+		for (int f = 0; f < 2; f++) {
+			const uint8_t* src = (f ? P.out2 : P.out1) + (size_t)j * P.blobPitch;
+			uint8_t* dst = (f ? P.dense2 : P.dense1) + d[f];
+			const int nPieces = (len[f] + MV_PIECE - 1) / MV_PIECE;
+#pragma unroll 1
+			for (int p0 = 0; p0 < nPieces; p0 += MV_STAGES) {
+				const int np = min(MV_STAGES, nPieces - p0);
+				if (lane == 0) {
+					// the stages were read with ordinary loads a moment ago: order those before the asynchronous writes
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					for (int i = 0; i < np; i++) {
+						const int off = (p0 + i) * MV_PIECE;
+						const uint32_t bytes = (uint32_t)((min(MV_PIECE, len[f] - off) + 15) & ~15);
+						mbar_expect_tx(barS + 8u * i, bytes);
+						bulk_load(ringS + (uint32_t)(i * MV_STAGE_BYTES), src + off, bytes, barS + 8u * i);
+					}
+				}
+				for (int i = 0; i < np; i++) {
+					mbar_wait(barS + 8u * i, (phase >> i) & 1u);
+					const int off = (p0 + i) * MV_PIECE;
+					store_piece(ringS + (uint32_t)(i * MV_STAGE_BYTES), ring + i * MV_STAGE_BYTES, min(MV_PIECE, len[f] - off), dst + off, lane);
+					phase ^= 1u << i;
+				}
+				__syncwarp();
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 1: generation into per-ticket blobs
 // ---------------------------------------------------------------------------------------------
 template <int NCH, int QP>
@@ -1254,6 +1363,19 @@ cudaError_t launch_move_blobs(const GenParams& P, int smCount, cudaStream_t stre
 	if (cgrid * (CP_THREADS / 32) > P.nTiles) cgrid = (P.nTiles + CP_THREADS / 32 - 1) / (CP_THREADS / 32);
 	if (cgrid < 1) cgrid = 1;
 	move_blobs_kernel<<<cgrid, CP_THREADS, 0, stream>>>(P);
+	return cudaGetLastError();
+}
+
+// pass 2b on `ctas` SMs (see move_blobs_tma_kernel): meant to run on a second stream under the next batch's generation kernel
+cudaError_t launch_move_blobs_tma(const GenParams& P, int ctas, cudaStream_t stream) {
+	const int smem = MV_WARPS * MV_WARP_BYTES;
+	static bool attr = false;
+	if (!attr) {
+		cudaError_t e = cudaFuncSetAttribute(move_blobs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e != cudaSuccess) return e;
+		attr = true;
+	}
+	move_blobs_tma_kernel<<<ctas, MV_THREADS, smem, stream>>>(P);
 	return cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ cudaError_t launch_generate_fast(const GenParams& P, int qmode, size_t smemBytes
                                  cudaEvent_t e0, cudaEvent_t e1);
 cudaError_t launch_scan_blobs(const GenParams& P, cudaStream_t stream);
 cudaError_t launch_move_blobs(const GenParams& P, int smCount, cudaStream_t stream);
+cudaError_t launch_move_blobs_tma(const GenParams& P, int ctas, cudaStream_t stream);
 cudaError_t launch_issue_floor(int mode, int RL, int64_t nPairs, uint64_t seed, int grid, uint32_t* scratch, uint8_t* blobs,
                                uint32_t blobPitch, uint32_t file2Off, cudaStream_t stream);   // floor.cu
 cudaError_t launch_pass2(const GenParams& P, int smCount, cudaStream_t stream);

@@ -79,7 +79,10 @@ struct Snp { long long pos; char nucleotide; };
 struct Target { long spos, epos; };
 
 struct Bin { long spos, epos; int hap; double weight; int rc; };
-struct Poke { int hap; long off; char c; };   // substitution at offset off of every copy of the reference slice
+struct Poke { int hap; long off; char c; };
+// A haplotype of a segment with insertion / deletion variants as a splice list: runs of the reference slice (copy t, bases
+// [a, b) of the slice) and literal runs (inserted sequences), in order.  The device assembles it from the uploaded chromosome.
+struct Piece { int copy; long a, b; std::string lit; long len() const { return copy >= 0 ? b - a : (long)lit.size(); } };   // substitution at offset off of every copy of the reference slice
 struct BinSpec { long spos, epos; int hap; int kind; long n; long gcStart, gcLen; };   // a bin before its GC draw (host_plan.cpp)
 struct ChrLayout {   // where the haplotype strings of one chromosome live in the device store
 	std::vector<std::vector<int64_t>> base;      // [segment][haplotype] store index of the string, -1 = absent
@@ -128,6 +131,8 @@ public:
 	void phase_segment(Segment& seg);                        // rand()-driven copy-number phasing (Segment.cpp:140-215)
 	bool segment_is_copy_only(const Segment& seg, const std::string& popu);
 	void segment_copies_and_pokes(Segment& seg, const std::string& popu, std::vector<int>& reps, std::vector<Poke>& pokes);
+	// the insert / erase part of Segment::generateSegSequences (Segment.cpp:313-444) on splice lists instead of strings
+	void segment_splices(Segment& seg, const std::string& popu, size_t refLen, const std::vector<int>& reps, std::vector<std::vector<Piece>>& ropes);
 	// bins + weights (Segment::getWeightedLength, Segment.cpp:550-641)
 	double weighted_length(Segment& seg, const std::string& popu);
 	double weighted_length_from(Segment& seg, const std::vector<std::string>& haps);

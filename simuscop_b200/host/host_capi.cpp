@@ -169,6 +169,50 @@ int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_pa
 	return job->job.prepare_sample(s, dev, dump_path ? dump_path : "", planned, emitted);
 }
 
+int ssh_selftest_splices(ssh_job* job, int64_t* segments_checked, int64_t* with_indels) {
+	// Host-only check of the splice-list construction the device path uses for segments with insertion / deletion variants
+	// (Job::segment_splices + the substitution mapping of Job::device_weights) against the string construction
+	// (Job::build_haplotypes, which the CPU suite pins against the instrumented reference): every haplotype of every segment
+	// of every population, materialised from its splice list, must equal the string.  Returns the number of mismatches.
+	if (!job) return -1;
+	sschost::Job& J = job->job;
+	J.begin_plan();
+	const int ploidy = J.cfg.num["ploidy"];
+	int64_t bad = 0, checked = 0, indel = 0;
+	for (auto& popu : J.cfg.popu)
+		for (auto& chr : J.chroms) {
+			const std::string& chrSeq = J.fasta.chromosome(chr);
+			for (auto& seg : J.segs[popu][chr]) {
+				std::vector<std::string> want;
+				J.build_haplotypes(seg, popu, want);
+				const size_t refOff = (size_t)(seg.start - 1);
+				const size_t refLen = std::min((size_t)seg.refSize(), chrSeq.size() > refOff ? chrSeq.size() - refOff : 0);
+				if (refLen == 0) continue;
+				std::vector<int> reps; std::vector<sschost::Poke> pokes;
+				J.segment_copies_and_pokes(seg, popu, reps, pokes);
+				std::vector<std::vector<sschost::Piece>> ropes;
+				J.segment_splices(seg, popu, refLen, reps, ropes);
+				if (!J.segment_is_copy_only(seg, popu)) indel++;
+				for (int h = 0; h < ploidy; h++) {
+					std::string got;
+					std::vector<std::pair<size_t, char>> pk;
+					for (const sschost::Piece& p : ropes[h]) {
+						if (p.copy >= 0) {
+							for (const sschost::Poke& q : pokes) if (q.hap == h && q.off >= p.a && q.off < p.b) pk.push_back({got.size() + (size_t)(q.off - p.a), q.c});
+							got.append(chrSeq, refOff + (size_t)p.a, (size_t)(p.b - p.a));
+						} else got += p.lit;
+					}
+					for (auto& q : pk) got[q.first] = (char)toupper((unsigned char)q.second);
+					checked++;
+					if (got != want[h]) bad++;
+				}
+			}
+		}
+	if (segments_checked) *segments_checked = checked;
+	if (with_indels) *with_indels = indel;
+	return (int)bad;
+}
+
 int ssh_writer_open(const char* path1, const char* path2, int threads, ssh_writer** out) {
 	if (!path1 || !out) return SSC_ERR_INVALID;
 	ssh_writer* w = new ssh_writer();

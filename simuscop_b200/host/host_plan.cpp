@@ -9,6 +9,7 @@
 #include <thread>
 #include <cstring>
 #include <iostream>
+#include <stdexcept>
 
 #include "host.h"
 
@@ -362,6 +363,105 @@ void Job::segment_copies_and_pokes(Segment& seg, const std::string& popu, std::v
 		}
 }
 
+namespace {
+// std::string::insert / erase semantics on a splice list (including their out_of_range behaviour, which the string path has
+// through the standard library)
+long rope_len(const std::vector<Piece>& r) { long n = 0; for (const Piece& p : r) n += p.len(); return n; }
+
+// index of the piece that starts exactly at pos after splitting (pos <= length)
+size_t rope_split(std::vector<Piece>& r, long pos) {
+	long at = 0;
+	for (size_t i = 0; i < r.size(); i++) {
+		const long n = r[i].len();
+		if (pos == at) return i;
+		if (pos < at + n) {
+			Piece left = r[i], right = r[i];
+			const long cut = pos - at;
+			if (left.copy >= 0) { left.b = left.a + cut; right.a = left.b; }
+			else { left.lit = r[i].lit.substr(0, (size_t)cut); right.lit = r[i].lit.substr((size_t)cut); }
+			r[i] = left;
+			r.insert(r.begin() + (long)i + 1, right);
+			return i + 1;
+		}
+		at += n;
+	}
+	return r.size();
+}
+
+void rope_insert(std::vector<Piece>& r, long pos, const std::string& seq) {
+	if (pos < 0 || pos > rope_len(r)) throw std::out_of_range("basic_string::insert");
+	const size_t i = rope_split(r, pos);
+	Piece p; p.copy = -1; p.a = p.b = 0; p.lit = seq;
+	r.insert(r.begin() + (long)i, p);
+}
+
+void rope_erase(std::vector<Piece>& r, long pos, long n) {
+	const long total = rope_len(r);
+	if (pos < 0 || pos > total) throw std::out_of_range("basic_string::erase");
+	if (n < 0) n = total - pos;                       // (size_t)len of a negative length: to the end, as the string path
+	n = std::min(n, total - pos);
+	if (n <= 0) return;
+	const size_t i = rope_split(r, pos);
+	const size_t j = rope_split(r, pos + n);
+	r.erase(r.begin() + (long)i, r.begin() + (long)j);
+}
+}  // namespace
+
+// Insertions and deletions of a segment applied to splice lists: the same order, positions and offset bookkeeping as
+// Job::build_haplotypes (Segment.cpp:313-444), with string insert / erase replaced by their splice-list forms.  The SNP / SNV
+// substitutions, which the reference applies first, do not move any base: they are mapped onto the final layout afterwards
+// (device_weights).
+void Job::segment_splices(Segment& seg, const std::string& popu, size_t refLen, const std::vector<int>& reps, std::vector<std::vector<Piece>>& ropes) {
+	const int ploidy = cfg.num["ploidy"];
+	const unsigned int refSize = (unsigned int)refLen;
+	auto inM = [&](int j) { return std::find(seg.mIndx.begin(), seg.mIndx.end(), j) != seg.mIndx.end(); };
+	ropes.assign(ploidy, std::vector<Piece>());
+	for (int i = 0; i < ploidy; i++)
+		for (int t = 0; t < reps[i]; t++) { Piece p; p.copy = t; p.a = 0; p.b = (long)refLen; ropes[i].push_back(p); }
+	std::vector<std::map<int, int>> insMap(ploidy), delMap(ploidy);
+	std::vector<int> insLens(ploidy, 0), delLens(ploidy, 0);
+	int k = 0;
+	for (const Ins& in : inss[popu][seg.chr]) {
+		if (in.pos >= seg.start && in.pos <= seg.end) {
+			int sindx = (int)(in.pos + 1 - seg.start);
+			int len = (int)in.seq.length();
+			for (int j = 0; j < ploidy; j++) {
+				if (in.het && ((k == 0 && !inM(j)) || (k == 1 && inM(j)))) continue;
+				int offset = 0;
+				for (auto& kv : insMap[j]) if (kv.first <= sindx) offset += kv.second;
+				std::vector<Piece>& h = ropes[j];
+				int n = (int)(rope_len(h) / (refSize + insLens[j]));
+				for (int t = 0; t < n; t++) rope_insert(h, (long)(sindx + offset + t * (refSize + insLens[j] + len)), in.seq);
+				insLens[j] += len;
+				insMap[j].insert(std::make_pair(sindx, len));
+			}
+			if (in.het) k = (k + 1) % 2;
+		}
+	}
+	k = 0;
+	for (const Del& d : dels[popu][seg.chr]) {
+		if (d.pos >= seg.start && d.pos <= seg.end) {
+			int sindx = (int)(d.pos - seg.start);
+			for (int j = 0; j < ploidy; j++) {
+				if (d.het && ((k == 0 && !inM(j)) || (k == 1 && inM(j)))) continue;
+				int offset = 0;
+				for (auto& kv : insMap[j]) if (kv.first <= sindx) offset += kv.second;
+				for (auto& kv : delMap[j]) if (kv.first <= sindx) offset -= kv.second;
+				if (sindx + offset < 0) continue;
+				std::vector<Piece>& h = ropes[j];
+				int n = (int)(rope_len(h) / (refSize + insLens[j] - delLens[j]));
+				for (int t = 0; t < n; t++) rope_erase(h, (long)(sindx + offset + t * (refSize + insLens[j] - delLens[j] - d.len)), (long)d.len);
+				delLens[j] += d.len;
+				delMap[j].insert(std::make_pair(sindx, d.len));
+			}
+			if (d.het) k = (k + 1) % 2;
+		}
+	}
+	for (auto& h : ropes)
+		for (Piece& p : h)
+			if (p.copy < 0) std::transform(p.lit.begin(), p.lit.end(), p.lit.begin(), [](unsigned char c) { return (char)toupper(c); });
+}
+
 // Device mode of the weights pass: the haplotype strings of one population are built chromosome by chromosome, appended
 // to the haplotype store(s) in contig order (for every haplotype index, the segments' strings in order) and dropped; the
 // GC percentages of all bins of the chromosome come from ssc_gc_census on the packed store.  Same bins, same draws in
@@ -378,15 +478,15 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		L.hapLen.assign(v.size(), std::vector<size_t>(ploidy, 0));
 		L.contigEnd.assign(ploidy, 0);
 		double t0 = PhaseTimers::now();
-		// segments without indel variants are built on the device from the uploaded chromosome (copies + substitutions);
-		// the others as host strings (Segment::generateSegSequences' insert / erase arithmetic stays on the host)
-		// The chromosome goes to the device straight from the FASTA file (raw lines -> pinned staging -> unfold kernel); the
-		// host reads and upper-cases it only when it needs the string itself: a segment with insertion / deletion variants,
-		// or IUPAC codes in the record (the count comes back from the unfold kernel).
+		// The chromosome goes to the device straight from the FASTA file (raw lines -> pinned staging -> unfold kernel) and every
+		// haplotype is assembled there: copies of the segment's reference slice per copy-number phasing, for segments with
+		// insertion / deletion variants as a splice list of slice runs and inserted literals (Segment::generateSegSequences'
+		// insert / erase arithmetic runs on the list instead of on strings), SNP / SNV alleles poked in afterwards.  The host
+		// reads and upper-cases the chromosome only when it needs the string itself: IUPAC codes in the record (the count
+		// comes back from the unfold kernel), in an inserted sequence or in an allele.
 		const FastaEntry* fe = fasta.entry(chr);
 		const size_t chrLen = fe ? (size_t)fe->length : 0;
 		bool needHost = !useRefBuild || !fe || fe->line_blen <= 0;
-		for (size_t k = 0; k < v.size() && !needHost; k++) if (!segment_is_copy_only(v[k], popu)) needHost = true;
 		bool devRef = false;
 		if (useRefBuild && fe && fe->line_blen > 0 && chrLen > 0) {
 			const uint64_t lines = (uint64_t)((chrLen - 1) / (size_t)fe->line_blen);          // full lines in front of the last one
@@ -405,6 +505,7 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		std::vector<std::vector<std::string>> haps(v.size());
 		std::vector<std::vector<int>> reps(v.size());
 		std::vector<std::vector<Poke>> pokes(v.size());
+		std::vector<std::vector<std::vector<Piece>>> ropes(v.size());      // [segment][haplotype]: splice lists of the segments with indel variants
 		std::vector<char> onDev(v.size(), 0), hostGc(v.size(), 0);
 		std::vector<size_t> refOffs(v.size(), 0), refLens(v.size(), 0);
 		bool anyDev = false;
@@ -417,14 +518,22 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 			// codes in the FASTA, in an inserted sequence or in an allele) keeps its strings on the host and gets its GC
 			// percentages from gc_percent() below.
 			bool exotic = needHost && fasta.other_in(refOff, refOff + refLen);
-			if (!exotic && useRefBuild && refLen > 0 && segment_is_copy_only(v[k], popu)) {
+			if (!exotic && useRefBuild && refLen > 0) {
 				segment_copies_and_pokes(v[k], popu, reps[k], pokes[k]);
 				for (const Poke& pk : pokes[k]) exotic |= !is_acgtn(pk.c);
+				if (!exotic && !segment_is_copy_only(v[k], popu)) {
+					segment_splices(v[k], popu, refLen, reps[k], ropes[k]);
+					for (auto& r : ropes[k]) for (const Piece& p : r) if (p.copy < 0) for (char c : p.lit) exotic |= !is_acgtn(c);
+				}
 				if (!exotic) {
-					for (int h = 0; h < ploidy; h++) L.hapLen[k][h] = refLen * (size_t)reps[k][h];
+					for (int h = 0; h < ploidy; h++) {
+						if (ropes[k].empty()) L.hapLen[k][h] = refLen * (size_t)reps[k][h];
+						else { size_t n = 0; for (const Piece& p : ropes[k][h]) n += (size_t)p.len(); L.hapLen[k][h] = n; }
+					}
 					onDev[k] = 1; anyDev = true;
 					continue;
 				}
+				ropes[k].clear();
 			}
 			if (!needHost) fasta.chromosome(chr);          // (an exotic allele on a chromosome that was not needed on the host so far)
 			build_haplotypes(v[k], popu, haps[k]);
@@ -442,11 +551,28 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 			for (size_t k = 0; k < v.size(); k++) {
 				if (L.hapLen[k][h] == 0) continue;
 				uint64_t first = localSize;
-				if (onDev[k]) {
+				if (onDev[k] && ropes[k].empty()) {
 					for (ssc_handle* dev : devs) { rc = ssc_genome_append_ref(dev, refOffs[k], refLens[k], reps[k][h], &first); if (rc) return rc; }
 					for (const Poke& pk : pokes[k])
 						if (pk.hap == h && (size_t)pk.off < refLens[k])
 							for (int t = 0; t < reps[k][h]; t++) { pokePos.push_back((int64_t)(first + (uint64_t)pk.off + (uint64_t)t * refLens[k])); pokeChr.push_back(pk.c); }
+				} else if (onDev[k]) {
+					// splice list: slice runs from the uploaded chromosome, literal runs from the host; a substitution lands on
+					// every surviving run of the slice that holds its base (one per copy unless a deletion took it)
+					uint64_t at = localSize;
+					for (const Piece& p : ropes[k][h]) {
+						const uint64_t n = (uint64_t)p.len();
+						if (n == 0) continue;
+						uint64_t f = at;
+						for (ssc_handle* dev : devs) {
+							rc = p.copy >= 0 ? ssc_genome_append_ref(dev, refOffs[k] + (uint64_t)p.a, n, 1, &f) : ssc_genome_append(dev, p.lit.data(), n, &f);
+							if (rc) return rc;
+						}
+						if (p.copy >= 0)
+							for (const Poke& pk : pokes[k])
+								if (pk.hap == h && pk.off >= p.a && pk.off < p.b) { pokePos.push_back((int64_t)(f + (uint64_t)(pk.off - p.a))); pokeChr.push_back(pk.c); }
+						at = f + n;
+					}
 				} else {
 					for (ssc_handle* dev : devs) { rc = ssc_genome_append(dev, haps[k][h].data(), haps[k][h].size(), &first); if (rc) return rc; }
 				}

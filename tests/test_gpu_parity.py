@@ -32,12 +32,13 @@ def test_fastq_bit_exact_vs_instrumented_reference(name, gen, workdir):
         assert len(r1) > 0
 
 
-@pytest.mark.parametrize("mode", ["force_generic", "fp64_search", "no_splice", "no_q16", "carry_pass2"])
+@pytest.mark.parametrize("mode", ["force_generic", "fp64_search", "no_splice", "no_q16", "carry_pass2", "concurrent_move"])
 @pytest.mark.parametrize("name", ["pe_xten", "pe_tiny", "se_gaiix"])
 def test_fallback_kernels_bit_exact(name, mode, built, workdir):
     """The generic integer kernel, the FP64 linear-search ground-truth kernel, the fast kernel without the spliced indel path,
     without the 16-bit-key shared-memory tables (profiles with 9..40 live quality symbols then keep only the ref == call rows
-    in shared memory) and with pass 2 carried by the next batch's generation kernel all give the same bytes."""
+    in shared memory), with pass 2 carried by the next batch's generation kernel, and with pass 2 on the bulk-copy mover
+    (8 SMs, second stream, under the next batch's generation) all give the same bytes."""
     from simuscop_b200 import cuda_binding
     scn = helpers.build_scenario(name, workdir)
     plans, out = helpers.run_reference_philox(scn, tag=mode)
@@ -46,8 +47,8 @@ def test_fallback_kernels_bit_exact(name, mode, built, workdir):
     r1, r2 = helpers.read_file(r1p), helpers.read_file(r2p)
     g = cuda_binding.Generator(0)
     try:
-        g.set_option(mode, 1)
-        if mode == "carry_pass2":
+        g.set_option(mode, 8 if mode == "concurrent_move" else 1)
+        if mode in ("carry_pass2", "concurrent_move"):
             g.set_option("batch_pairs", 256)          # many batches: every launch but the first moves its predecessor's blobs
         g.load_plan(plan, scn["seed"])
         f1, f2 = g.generate()

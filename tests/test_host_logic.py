@@ -378,3 +378,34 @@ def test_file_writer_sink_writes_ordered_slabs(built, tmp_path):
         else:
             assert not os.path.exists(p2)
     assert hl.ssh_writer_open(str(tmp_path / "no" / "such" / "dir.fq").encode(), None, 2, C.byref(C.c_void_p())) != 0
+
+
+@pytest.mark.parametrize("kind,seed", [("scenario", "pe_variants"), ("scenario", "se_tumor"), ("scenario", "pe_ploidy3"), ("scenario", "pe_iupac")] +
+                         [("fuzz", s) for s in (11, 12, 13, 14, 15, 16, 21, 22, 23)] + [("edge", s) for s in (0, 1, 3, 5, 6, 7, 14, 17)])
+def test_splice_lists_equal_haplotype_strings(kind, seed, built, workdir):
+    """Segments with insertion / deletion variants are assembled on the device from splice lists (runs of the reference slice
+    + inserted literals, substitutions mapped onto the surviving runs).  Materialised on the host, every such list must give
+    the haplotype string of the string construction -- which the plan-dump tests pin against the instrumented reference --
+    for CNV gains / losses with tandem copies, homo- and heterozygous indels and SNVs, SNPs, indels at segment edges and
+    inside CNVs, triploid genomes, tumour populations."""
+    from simuscop_b200 import host_binding
+    if kind == "scenario":
+        scn = helpers.build_scenario(seed, workdir)
+    elif kind == "fuzz":
+        scn = helpers.build_random_variation_scenario(seed, workdir)
+    else:
+        scn, _ = helpers.build_edge_variation_scenario(seed, workdir)
+    cfg = os.path.join(scn["dir"], "cfg_splice.txt")
+    synth.write_config(cfg, output=os.path.join(scn["dir"], "out_splice"), **scn["kw"])
+    hl = host_binding.lib()
+    hl.ssh_selftest_splices.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    # (a config the front end rejects exits the process, like the reference: run the check in a child)
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); from simuscop_b200 import host_binding as hb; j = hb.Job(%r, %d); "
+            "hl = hb.lib(); hl.ssh_selftest_splices.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]; "
+            "n, k = C.c_int64(), C.c_int64(); bad = hl.ssh_selftest_splices(j.j, C.byref(n), C.byref(k)); print('RESULT', bad, n.value, k.value)"
+            % (paths.ROOT, cfg, scn["seed"]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=scn["dir"])
+    if r.returncode != 0:
+        pytest.skip("input rejected by the front end (as by the reference): %s" % r.stderr.strip().split("\n")[-1][:120])
+    bad, n, k = [int(x) for x in [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()[1:]]
+    assert bad == 0 and n > 0, (bad, n, k)
