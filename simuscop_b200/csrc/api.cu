@@ -74,8 +74,9 @@ struct ssc_handle {
 	bool forceGeneric = false;
 	bool noSplice = false;        // tests: see GenParams::noSplice
 	int maxCtas = 0;              // > 0: cap the grid of the generation kernel (tests: many tickets per warp on small inputs)
-	int moverCtas = 0;            // "concurrent_move" > 0: pass 2b of batch k runs on that many SMs (bulk-copy mover, second stream) under the
-	                              // generation kernel of batch k+1, which leaves them free
+	int moverCtas = -1;           // "concurrent_move": pass 2b of batch k runs on that many SMs (bulk-copy mover, second stream) under the
+	                              // generation kernel of batch k+1, which leaves them free.  -1 = default: 8 of 148 SMs (measured
+	                              // optimum on the 3 Gb job: 4.30 -> 3.97 ms per step; 6 SMs cannot keep up, 12 cost the generation more)
 	cudaStream_t mover = nullptr;
 	cudaEvent_t evPre = nullptr, evScanned[2] = {nullptr, nullptr}, evMoved[2] = {nullptr, nullptr};
 	bool noQ16 = false;           // "no_q16": keep profiles with 9..40 live quality symbols on the diagonal-rows mode (A/B, tests)
@@ -427,6 +428,7 @@ static int init_handle(ssc_handle* h, int device) {
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, device));
 	h->smCount = prop.multiProcessorCount;
+	if (h->moverCtas < 0) h->moverCtas = h->smCount >= 64 ? (h->smCount * 8 + 74) / 148 : 0;
 	h->smemLimit = (int)prop.sharedMemPerBlockOptin - 1024;
 	CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
