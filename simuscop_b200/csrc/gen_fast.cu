@@ -62,7 +62,19 @@ struct FastLayout {
 
 __host__ __device__ inline FastLayout fast_layout(int subBytes, int qualBytes, int qualSymBytes, int nIsize, int nIns, int nDel) {
 	FastLayout L;
+	// per-warp scratch first, the LUT and the digit constants right behind it: their shared addresses are compile-time
+	// constants (plus warp * perWarp), which matters because the register-starved kernel recomputes them wherever it needs them
+	int w = 0;
+	L.w_ev = w; w += F_EV_MAX * 8;
+	L.w_insb = w; w += F_INS_CAP;
+	L.w_insp = w; w += 48;                          // inserted bases, packed: one pad word in front, 8 + 1 words
+	L.w_out = w; w += 80;                           // spliced (post-indel) read, packed like a window: one pad word in front, 16 + 1 words
+	L.w_win = w; w += 2 * F_WIN_WORDS * 4;          // one window per mate, filled by cp.async
+	L.perWarp = w;
 	int o = 0;
+	L.warp = o; o += FG_GEN * L.perWarp;
+	L.lut = o; o += F_LUT_N * 2;
+	L.dig = o; o += 32 * 16;                       // per-lane header digit constants
 	L.sub = o; o += (subBytes + 15) / 16 * 16;
 	L.qual = o; o += (qualBytes + 15) / 16 * 16;
 	L.qualSym = o; o += (qualSymBytes + 15) / 16 * 16;
@@ -72,16 +84,6 @@ __host__ __device__ inline FastLayout fast_layout(int subBytes, int qualBytes, i
 	L.insSym = o; o += (nIns * 2 + 15) / 16 * 16;
 	L.delT = o; o += (nDel * 4 + 15) / 16 * 16;
 	L.delSym = o; o += (nDel * 2 + 15) / 16 * 16;
-	L.lut = o; o += F_LUT_N * 2;
-	L.dig = o; o += 32 * 16;                       // per-lane header digit constants
-	int w = 0;
-	L.w_ev = w; w += F_EV_MAX * 8;
-	L.w_insb = w; w += F_INS_CAP;
-	L.w_insp = w; w += 48;                          // inserted bases, packed: one pad word in front, 8 + 1 words
-	L.w_out = w; w += 80;                           // spliced (post-indel) read, packed like a window: one pad word in front, 16 + 1 words
-	L.w_win = w; w += 2 * F_WIN_WORDS * 4;          // one window per mate, filled by cp.async
-	L.perWarp = w;
-	L.warp = o; o += FG_GEN * L.perWarp;
 	L.total = o;
 	return L;
 }
@@ -1096,31 +1098,27 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 			const int nameLen = (int)((nameNd >> 17) & 127u), nameOff = (int)(nameNd & 0x1ffffu);
 			const int H = nameLen + nd1 + 1 + nd2 + (t.paired ? 2 : 0) + 1;
 			const int hWords = (H + 31) >> 5;
+			const uint32_t slash = t.paired ? (uint32_t)'/' : (uint32_t)'\n';
+			const int mateAt = t.paired ? H - 2 : -1;
 #pragma unroll
 			for (int r = 0; r < 3; r++) {
 				if (r >= hWords) break;
+				// character i of the header: name | digits of pos % segsize (most significant first) | '#' | digits of the
+				// fragment counter | "/1\n" or "\n" -- selected without branches; the digits come from lanes 0..19 by shuffle
 				const int i = lane + 32 * r;
-				uint32_t ch = '\n';
-				int srcLane = 0;
-				if (i < nameLen) ch = (uint8_t)P.names[nameOff + i];
-				else {
-					const int k = i - nameLen;
-					if (k < nd1) { srcLane = nd1 - 1 - k; ch = 0; }
-					else if (k == nd1) ch = '#';
-					else {
-						const int k2 = k - nd1 - 1;
-						if (k2 < nd2) { srcLane = 10 + nd2 - 1 - k2; ch = 0; }
-						else if (t.paired && k2 == nd2) ch = '/';
-					}
-				}
-				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane);
+				const int k = i - nameLen, k2 = k - nd1 - 1;
+				const bool d1 = (unsigned)k < (unsigned)nd1, d2 = (unsigned)k2 < (unsigned)nd2;
+				const int srcLane = d1 ? nd1 - 1 - k : 9 + nd2 - k2;
+				const uint32_t dv = __shfl_sync(0xffffffffu, dg, srcLane & 31);
+				uint32_t ch = k == nd1 ? (uint32_t)'#' : (k2 == nd2 ? slash : (uint32_t)'\n');
+				ch = (d1 || d2) ? dv : ch;
+				if (r < 2 && k < 0) ch = (uint8_t)P.names[nameOff + i];          // names are at most 64 bytes
 				// straight into both records of the pair (the cursors of file 1 / file 2 are posA / posB here); only the mate
 				// digit in front of the final '\n' differs
 				if (i < H) {
-					const uint32_t hc = ch ? ch : dv;
-					const bool mateDigit = t.paired && i == H - 2;
-					P.out1[posA + i] = (uint8_t)(mateDigit ? '1' : hc);
-					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? '2' : hc);
+					const bool mateDigit = i == mateAt;
+					P.out1[posA + i] = (uint8_t)(mateDigit ? (uint32_t)'1' : ch);
+					if (t.paired) P.out1[posB + i] = (uint8_t)(mateDigit ? (uint32_t)'2' : ch);
 				}
 			}
 
