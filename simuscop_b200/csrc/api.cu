@@ -112,10 +112,11 @@ struct ssc_handle {
 	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
 	uint8_t* d_stage[2] = {nullptr, nullptr};
 	cudaEvent_t evStage[2] = {nullptr, nullptr};
-	static constexpr int FA_READERS = 4;          // ssc_reference_upload_fasta: reader threads, one pinned buffer each
-	uint8_t* h_fa[FA_READERS] = {nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t evFa[FA_READERS] = {nullptr, nullptr, nullptr, nullptr};
-	size_t faBytes = 16u << 20;
+	static constexpr int FA_READERS = 2;          // ssc_reference_upload_fasta: reader threads, one pinned buffer each (four readers
+	                                              // of 16 MB chunks were slower on the 16-vCPU boxes: 0.69 vs 0.28-0.31 s for the 3 Gb FASTA)
+	uint8_t* h_fa[FA_READERS] = {nullptr, nullptr};
+	cudaEvent_t evFa[FA_READERS] = {nullptr, nullptr};
+	size_t faBytes = 32u << 20;
 	size_t stageBytes = 32u << 20;
 
 	// plan
@@ -692,7 +693,7 @@ int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint
 	// c mod NR): the page-cache copy of pread is the slow part, so several run at a time, under the DMA of earlier chunks
 	// (and under the pack kernels of the previous chromosome that are still queued on the stream).
 	const uint64_t nChunks = (raw_len + h->faBytes - 1) / h->faBytes;
-	int rcs[ssc_handle::FA_READERS] = {SSC_OK, SSC_OK, SSC_OK, SSC_OK};
+	int rcs[ssc_handle::FA_READERS] = {SSC_OK, SSC_OK};
 	std::string errMsg[ssc_handle::FA_READERS];
 	auto feed = [&](int k) {
 		if (cudaSetDevice(h->device) != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = "cudaSetDevice failed"; return; }
@@ -1039,6 +1040,7 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 		int r = launch_batch(h, k & 1, batches[k].lo, batches[k].hi);
 		if (r) return r;
 		CK(cudaEventRecord(h->evGen[k & 1], h->compute));
+		if (!carried) CK(cudaEventRecord(h->evDense[k & 1], h->compute));     // the dense slab of batch k is complete with its own launch
 		return SSC_OK;
 	};
 	rc = launch(0);
@@ -1048,7 +1050,7 @@ int ssc_generate(ssc_handle* h, int64_t pair_lo, int64_t pair_hi, ssc_sink_fn si
 		const int buf = k & 1;
 		rc = k + 1 < nb ? launch(k + 1) : flush_pending(h);         // after this the dense slab of batch k is in the stream
 		if (rc) return bail(h, rc);
-		CK(cudaEventRecord(h->evDense[buf], h->compute));
+		if (carried) CK(cudaEventRecord(h->evDense[buf], h->compute));    // (its pass 2b came with the launch of batch k+1)
 		CK(cudaEventSynchronize(h->evGen[buf]));
 		res[buf] = *h->h_result[buf];
 		rc = check_result(h, res[buf]);
