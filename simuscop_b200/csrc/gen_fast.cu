@@ -781,41 +781,8 @@ __device__ __forceinline__ void store_piece(uint32_t st, const uint8_t* stGeneri
 	if (lane < n - t0) dst[t0 + lane] = stGeneric[t0 + lane];
 }
 
-// The pieces a warp moves, in order: tickets j0, j0 + nWarps, ..., of each ticket file 1 then file 2, of each blob its 4 KB
-// pieces.  Two of these walk the same sequence, the producer (bulk loads) up to MV_STAGES pieces ahead of the consumer
-// (stores); the lengths / offsets of the next ticket are fetched one ticket ahead.
-struct PieceIter {
-	int j, f, off, nWarps, nTiles;
-	unsigned long long excl, mine, nExcl, nMine;
-	__device__ __forceinline__ void fetch_next(const GenParams& P) {
-		const int jn = j + nWarps;
-		if (jn < nTiles) { nExcl = __ldcg(P.blobPrefix + jn); nMine = __ldcg(P.tileState + jn); }
-	}
-	__device__ __forceinline__ int len(int file) const { return file ? (int)(mine & 0x7fffffffull) : (int)(mine >> 31); }
-	__device__ __forceinline__ unsigned long long dstOff(int file) const { return file ? (excl & 0x7fffffffull) : (excl >> 31); }
-	__device__ __forceinline__ bool ticket_ok(const GenParams& P) const {      // blobs flagged by the scan (slab overflow) are skipped
-		return dstOff(0) + (unsigned)len(0) <= P.cap1 && dstOff(1) + (unsigned)len(1) <= P.cap2;
-	}
-	// position on the first piece at or after (j, f, off); false when the sequence is exhausted
-	__device__ __forceinline__ bool settle(const GenParams& P) {
-		while (j < nTiles) {
-			if (ticket_ok(P)) {
-				while (f < 2) { if (off < len(f)) return true; f++; off = 0; }
-			}
-			j += nWarps; f = 0; off = 0;
-			excl = nExcl; mine = nMine;
-			if (j < nTiles) fetch_next(P);
-		}
-		return false;
-	}
-	__device__ __forceinline__ void init(const GenParams& P, int j0, int nW) {
-		j = j0; f = 0; off = 0; nWarps = nW; nTiles = P.nTiles; excl = mine = nExcl = nMine = 0;
-		if (j < nTiles) { excl = __ldcg(P.blobPrefix + j); mine = __ldcg(P.tileState + j); fetch_next(P); }
-	}
-	__device__ __forceinline__ int bytes() const { return min(MV_PIECE, len(f) - off); }
-	__device__ __forceinline__ void step() { off += MV_PIECE; }
-};
-
+// (A continuous ring of pieces across blobs -- the next load issued as soon as a stage is stored -- was measured too: no
+// faster, 4.10 vs 3.97 ms per step on 8 SMs; an SM moves 45-50 GB/s each way either way.)
 __global__ void __launch_bounds__(MV_THREADS, 1) move_blobs_tma_kernel(const GenParams P) {
 	extern __shared__ __align__(128) uint8_t mv_smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -827,38 +794,40 @@ __global__ void __launch_bounds__(MV_THREADS, 1) move_blobs_tma_kernel(const Gen
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncwarp();
-	const int nWarps = gridDim.x * MV_WARPS, j0 = blockIdx.x * MV_WARPS + warp;
-	PieceIter prod, cons;
-	prod.init(P, j0, nWarps);
-	cons = prod;
 	uint32_t phase = 0;                               // one parity bit per stage
-	int issued = 0, consumed = 0;
-	auto issue = [&](int stage) {
-		// (all lanes walk the iterator, lane 0 talks to the copy engine)
-		const int n = prod.bytes();
-		if (lane == 0) {
-			const uint8_t* src = (prod.f ? P.out2 : P.out1) + (size_t)prod.j * P.blobPitch + prod.off;
-			const uint32_t bytes = (uint32_t)((n + 15) & ~15);
-			// the stage was read with ordinary loads a moment ago: order those before the asynchronous write
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			mbar_expect_tx(barS + 8u * stage, bytes);
-			bulk_load(ringS + (uint32_t)(stage * MV_STAGE_BYTES), src, bytes, barS + 8u * stage);
+	const int nWarps = gridDim.x * MV_WARPS;
+	for (int j = blockIdx.x * MV_WARPS + warp; j < P.nTiles; j += nWarps) {
+		const unsigned long long excl = __ldcg(P.blobPrefix + j), mine = __ldcg(P.tileState + j);
+		const unsigned long long d[2] = {excl >> 31, excl & 0x7fffffffull};
+		const int len[2] = {(int)(mine >> 31), (int)(mine & 0x7fffffffull)};
+		if (d[0] + (unsigned)len[0] > P.cap1 || d[1] + (unsigned)len[1] > P.cap2) continue;   // flagged by the scan
+#pragma unroll 1
+		for (int f = 0; f < 2; f++) {
+			const uint8_t* src = (f ? P.out2 : P.out1) + (size_t)j * P.blobPitch;
+			uint8_t* dst = (f ? P.dense2 : P.dense1) + d[f];
+			const int nPieces = (len[f] + MV_PIECE - 1) / MV_PIECE;
+#pragma unroll 1
+			for (int p0 = 0; p0 < nPieces; p0 += MV_STAGES) {
+				const int np = min(MV_STAGES, nPieces - p0);
+				if (lane == 0) {
+					// the stages were read with ordinary loads a moment ago: order those before the asynchronous writes
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					for (int i = 0; i < np; i++) {
+						const int off = (p0 + i) * MV_PIECE;
+						const uint32_t bytes = (uint32_t)((min(MV_PIECE, len[f] - off) + 15) & ~15);
+						mbar_expect_tx(barS + 8u * i, bytes);
+						bulk_load(ringS + (uint32_t)(i * MV_STAGE_BYTES), src + off, bytes, barS + 8u * i);
+					}
+				}
+				for (int i = 0; i < np; i++) {
+					mbar_wait(barS + 8u * i, (phase >> i) & 1u);
+					const int off = (p0 + i) * MV_PIECE;
+					store_piece(ringS + (uint32_t)(i * MV_STAGE_BYTES), ring + i * MV_STAGE_BYTES, min(MV_PIECE, len[f] - off), dst + off, lane);
+					phase ^= 1u << i;
+				}
+				__syncwarp();
+			}
 		}
-		prod.step();
-	};
-	for (int sIdx = 0; sIdx < MV_STAGES; sIdx++)
-		if (prod.settle(P)) { issue(sIdx); issued++; }
-	while (consumed < issued) {
-		const int stage = consumed % MV_STAGES;
-		cons.settle(P);
-		mbar_wait(barS + 8u * stage, (phase >> stage) & 1u);
-		phase ^= 1u << stage;
-		uint8_t* dst = (cons.f ? P.dense2 : P.dense1) + cons.dstOff(cons.f) + cons.off;
-		store_piece(ringS + (uint32_t)(stage * MV_STAGE_BYTES), ring + stage * MV_STAGE_BYTES, cons.bytes(), dst, lane);
-		cons.step();
-		consumed++;
-		__syncwarp();
-		if (prod.settle(P)) { issue(stage); issued++; }
 	}
 }
 
