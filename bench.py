@@ -374,7 +374,9 @@ def main():
     # ---------------- end to end INCLUDING the host write: the sink is the ordered file writer of the drop-in CLI
     # (libsimuscop_host: every slab pwrite()n by a small thread pool at its final offset), both FASTQ files
     file_legs = []
-    if not a.no_file:
+    # (one GPU only: the host write is a property of the box, not of the GPU count -- 4 to 7 GB/s on this pool -- and N ranks
+    # writing N x 28 GB at once would fill the box's tmpfs / RAM)
+    if not a.no_file and world == 1:
         hl = host_binding.lib()
         hl.ssh_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         hl.ssh_writer_sink.restype = C.c_void_p
