@@ -1144,8 +1144,8 @@ __global__ void __launch_bounds__(FG_THREADS, 1) generate_slots_kernel(const __g
 
 				// ---- phase A: one Philox block per cycle (chunks interleaved); indel candidates at reference position j
 				uint32_t x0[NCH], x1[NCH], x2[NCH], x3[NCH];
-				philox_chunks<NCH>(w.c0, w.c1, c2cyc, (uint32_t)lane, P.rk, x0, x1, x2, x3);
 				bool cand = false;
+				philox_chunks<NCH>(w.c0, w.c1, c2cyc, (uint32_t)lane, P.rk, x0, x1, x2, x3);
 #pragma unroll
 				for (int c = 0; c < NCH; c++) {
 					const bool hit = (x0[c] < P.insLim) | (x1[c] < P.delLim);
