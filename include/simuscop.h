@@ -177,6 +177,13 @@ int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n);
  * neither ACGT nor N in either case (IUPAC codes). */
 int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
                                uint32_t line_bases, uint32_t line_width, uint64_t* n_other);
+/* The same in the background: ssc_reference_prefetch_fasta starts reading and unfolding a record into a second set of
+ * buffers (own thread, own stream) and returns; the caller goes on working with the current reference (ssc_genome_append_ref,
+ * ssc_gc_census, host work) and later calls ssc_reference_adopt_prefetched, which waits for the record and makes it the
+ * current reference.  One record may be in flight. */
+int ssc_reference_prefetch_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
+                                 uint32_t line_bases, uint32_t line_width);
+int ssc_reference_adopt_prefetched(ssc_handle* h, uint64_t* n_other);
 int ssc_genome_append_ref(ssc_handle* h, uint64_t ref_off, uint64_t len, int32_t reps, uint64_t* first_base);
 int ssc_genome_poke(ssc_handle* h, const int64_t* store_pos, const char* chars, int64_t n);
 int ssc_genome_read(ssc_handle* h, uint64_t start, uint64_t n, char* out);

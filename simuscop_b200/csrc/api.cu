@@ -108,14 +108,25 @@ struct ssc_handle {
 	DevBuf<uint8_t> d_ref;                        // ASCII chromosome for ssc_genome_append_ref
 	DevBuf<uint8_t> d_raw;                        // raw FASTA lines of the chromosome (ssc_reference_upload_fasta), grow-only
 	DevBuf<unsigned long long> d_other;
+	// ssc_reference_prefetch_fasta: the next record is read and unfolded into a second set of buffers by a background thread
+	// on its own stream while the caller works with the current reference; ssc_reference_adopt_prefetched swaps the sets
+	DevBuf<uint8_t> d_ref2, d_raw2;
+	DevBuf<unsigned long long> d_other2;
+	cudaStream_t upload = nullptr;
+	cudaEvent_t evRefFree = nullptr;
+	std::thread prefetchThread;
+	bool prefetching = false;
+	int prefetchRc = 0;
+	std::string prefetchErr;
+	uint64_t prefetchBases = 0, prefetchRaw = 0, prefetchOther = 0;
 	uint64_t refSize = 0;
 	uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned upload staging
 	uint8_t* d_stage[2] = {nullptr, nullptr};
 	cudaEvent_t evStage[2] = {nullptr, nullptr};
 	static constexpr int FA_READERS = 2;          // ssc_reference_upload_fasta: reader threads, one pinned buffer each (four readers
 	                                              // of 16 MB chunks were slower on the 16-vCPU boxes: 0.69 vs 0.28-0.31 s for the 3 Gb FASTA)
-	uint8_t* h_fa[FA_READERS] = {nullptr, nullptr};
-	cudaEvent_t evFa[FA_READERS] = {nullptr, nullptr};
+	uint8_t* h_fa[2 * FA_READERS] = {nullptr, nullptr, nullptr, nullptr};       // [0, FA_READERS): foreground, the rest: prefetch
+	cudaEvent_t evFa[2 * FA_READERS] = {nullptr, nullptr, nullptr, nullptr};
 	size_t faBytes = 32u << 20;
 	size_t stageBytes = 32u << 20;
 
@@ -471,6 +482,7 @@ int ssc_create(int device, ssc_handle** out) {
 
 int ssc_destroy(ssc_handle* h) {
 	if (!h) return SSC_OK;
+	if (h->prefetchThread.joinable()) h->prefetchThread.join();
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	for (int b = 0; b < 2; b++) {
@@ -480,7 +492,7 @@ int ssc_destroy(ssc_handle* h) {
 		}
 		if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
 		if (h->d_stage[b]) cudaFree(h->d_stage[b]);
-		for (int r = b; r < ssc_handle::FA_READERS; r += 2) {
+		for (int r = b; r < 2 * ssc_handle::FA_READERS; r += 2) {
 			if (h->h_fa[r]) cudaFreeHost(h->h_fa[r]);
 			if (h->evFa[r]) cudaEventDestroy(h->evFa[r]);
 		}
@@ -503,6 +515,9 @@ int ssc_destroy(ssc_handle* h) {
 	h->d_sub.release(); h->d_fIsize.release(); h->d_fIns.release(); h->d_fDel.release();
 	h->d_fSub1.release(); h->d_fSub2.release(); h->d_fQual.release(); h->d_lut.release();
 	h->d_hap2.release(); h->d_hapN.release(); h->d_ref.release(); h->d_raw.release(); h->d_other.release();
+	h->d_ref2.release(); h->d_raw2.release(); h->d_other2.release();
+	if (h->upload) cudaStreamDestroy(h->upload);
+	if (h->evRefFree) cudaEventDestroy(h->evRefFree);
 	h->d_ticket2.release(); h->d_gzLens.release();
 	for (int f = 0; f < 2; f++) if (h->d_gzBlobs[f]) cudaFree(h->d_gzBlobs[f]);
 	if (h->d_gzTab) cudaFree(h->d_gzTab);
@@ -672,45 +687,49 @@ int ssc_reference_upload(ssc_handle* h, const char* ascii, uint64_t n) {
 	return SSC_OK;
 }
 
-int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
-                               uint32_t line_bases, uint32_t line_width, uint64_t* n_other) {
-	if (!h || fd < 0) return fail(SSC_ERR_INVALID, "bad argument");
-	if (n_bases >= (1ull << 32) - 64 || (n_bases && (line_bases == 0 || line_width < line_bases)))
-		return fail(SSC_ERR_INVALID, "FASTA record geometry not supported (%llu bases, %u per line of %u bytes)",
-		            (unsigned long long)n_bases, line_bases, line_width);
+}  // extern "C"
+
+namespace {
+// One FASTA record: file -> pinned staging (pread) -> raw (device) -> unfold kernel -> ref (device); returns when the
+// unfolded record and the count of IUPAC characters are there.  `slot` 0 = the foreground set of staging buffers, 1 = the
+// prefetch set.  Thread-safe against a concurrent call on the other slot (nothing of the handle is shared but the device).
+int upload_fasta_record(ssc_handle* h, int slot, cudaStream_t s, DevBuf<uint8_t>& ref, DevBuf<uint8_t>& raw, DevBuf<unsigned long long>& otherBuf,
+                        cudaEvent_t waitFor, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases, uint32_t line_bases,
+                        uint32_t line_width, uint64_t* n_other) {
 	CK(cudaSetDevice(h->device));
-	if (h->d_ref.n < n_bases + 16) CK(h->d_ref.alloc((size_t)n_bases + (size_t)n_bases / 8 + 4096));
-	if (h->d_raw.n < raw_len) CK(h->d_raw.alloc((size_t)raw_len + (size_t)raw_len / 8 + 4096));
-	if (!h->d_other.p) CK(h->d_other.alloc(1));
-	const int NR = ssc_handle::FA_READERS;
-	for (int i = 0; i < NR; i++) {
+	if (ref.n < n_bases + 16) CK(ref.alloc((size_t)n_bases + (size_t)n_bases / 8 + 4096));
+	if (raw.n < raw_len) CK(raw.alloc((size_t)raw_len + (size_t)raw_len / 8 + 4096));
+	if (!otherBuf.p) CK(otherBuf.alloc(1));
+	const int NR = ssc_handle::FA_READERS, b0 = slot * NR;
+	for (int i = b0; i < b0 + NR; i++) {
 		if (!h->h_fa[i]) CK(cudaMallocHost((void**)&h->h_fa[i], h->faBytes));
 		if (!h->evFa[i]) CK(cudaEventCreateWithFlags(&h->evFa[i], cudaEventDisableTiming));
 	}
-	cudaStream_t s = h->compute;
-	CK(cudaMemsetAsync(h->d_other.p, 0, 8, s));
-	// file -> pinned staging (pread) -> device.  NR staging buffers, each fed by its own host thread (chunk c goes to reader
-	// c mod NR): the page-cache copy of pread is the slow part, so several run at a time, under the DMA of earlier chunks
-	// (and under the pack kernels of the previous chromosome that are still queued on the stream).
+	if (waitFor) CK(cudaStreamWaitEvent(s, waitFor, 0));         // earlier readers of `ref` (pack kernels of the record before the last)
+	CK(cudaMemsetAsync(otherBuf.p, 0, 8, s));
+	// NR staging buffers, each fed by its own host thread (chunk c goes to reader c mod NR): the page-cache copy of pread is the
+	// slow part, so two run at a time, under the DMA of earlier chunks
 	const uint64_t nChunks = (raw_len + h->faBytes - 1) / h->faBytes;
 	int rcs[ssc_handle::FA_READERS] = {SSC_OK, SSC_OK};
 	std::string errMsg[ssc_handle::FA_READERS];
 	auto feed = [&](int k) {
 		if (cudaSetDevice(h->device) != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = "cudaSetDevice failed"; return; }
+		uint8_t* buf = h->h_fa[b0 + k];
+		cudaEvent_t ev = h->evFa[b0 + k];
 		for (uint64_t c = (uint64_t)k; c < nChunks; c += NR) {
 			const uint64_t done = c * h->faBytes;
 			const size_t chunk = (size_t)std::min<uint64_t>(h->faBytes, raw_len - done);
-			cudaError_t e = cudaEventSynchronize(h->evFa[k]);             // staging buffer k free again
+			cudaError_t e = cudaEventSynchronize(ev);                     // staging buffer free again
 			size_t got = 0;
 			while (e == cudaSuccess && got < chunk) {
-				const ssize_t r = pread(fd, h->h_fa[k] + got, chunk - got, (off_t)(file_offset + done + got));
+				const ssize_t r = pread(fd, buf + got, chunk - got, (off_t)(file_offset + done + got));
 				if (r < 0) { if (errno == EINTR) continue; rcs[k] = SSC_ERR_INVALID; errMsg[k] = std::string("reading the FASTA file failed: ") + strerror(errno); return; }
 				if (r == 0) break;                                         // a last line without a line feed ends the file early
 				got += (size_t)r;
 			}
-			if (got < chunk) memset(h->h_fa[k] + got, '\n', chunk - got);
-			if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_raw.p + done, h->h_fa[k], chunk, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess) e = cudaEventRecord(h->evFa[k], s);
+			if (got < chunk) memset(buf + got, '\n', chunk - got);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(raw.p + done, buf, chunk, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess) e = cudaEventRecord(ev, s);
 			if (e != cudaSuccess) { rcs[k] = SSC_ERR_CUDA; errMsg[k] = std::string("staging the FASTA record failed: ") + cudaGetErrorString(e); return; }
 		}
 	};
@@ -721,14 +740,71 @@ int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint
 		for (auto& t : readers) t.join();
 	}
 	for (int k = 0; k < NR; k++) if (rcs[k]) return fail(rcs[k], "%s", errMsg[k].c_str());
-	h->stats.h2d_bytes += raw_len;
-	CK(ssc::launch_unfold(h->d_raw.p, raw_len, n_bases, line_bases, line_width, h->d_ref.p, h->d_other.p, s));
+	CK(ssc::launch_unfold(raw.p, raw_len, n_bases, line_bases, line_width, ref.p, otherBuf.p, s));
 	unsigned long long other = 0;
-	CK(cudaMemcpyAsync(&other, h->d_other.p, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(&other, otherBuf.p, 8, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
-	h->refSize = n_bases;
-	h->stats.launches += 1;
 	if (n_other) *n_other = other;
+	return SSC_OK;
+}
+
+int check_fasta_geometry(uint64_t n_bases, uint32_t line_bases, uint32_t line_width) {
+	if (n_bases >= (1ull << 32) - 64 || (n_bases && (line_bases == 0 || line_width < line_bases)))
+		return fail(SSC_ERR_INVALID, "FASTA record geometry not supported (%llu bases, %u per line of %u bytes)",
+		            (unsigned long long)n_bases, line_bases, line_width);
+	return SSC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ssc_reference_upload_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
+                               uint32_t line_bases, uint32_t line_width, uint64_t* n_other) {
+	if (!h || fd < 0) return fail(SSC_ERR_INVALID, "bad argument");
+	if (h->prefetching) return fail(SSC_ERR_STATE, "a prefetched FASTA record is waiting: adopt it first");
+	int rc = check_fasta_geometry(n_bases, line_bases, line_width);
+	if (rc) return rc;
+	rc = upload_fasta_record(h, 0, h->compute, h->d_ref, h->d_raw, h->d_other, nullptr, fd, file_offset, raw_len, n_bases, line_bases, line_width, n_other);
+	if (rc) return rc;
+	h->refSize = n_bases;
+	h->stats.h2d_bytes += raw_len;
+	h->stats.launches += 1;
+	return SSC_OK;
+}
+
+int ssc_reference_prefetch_fasta(ssc_handle* h, int fd, uint64_t file_offset, uint64_t raw_len, uint64_t n_bases,
+                                 uint32_t line_bases, uint32_t line_width) {
+	if (!h || fd < 0) return fail(SSC_ERR_INVALID, "bad argument");
+	if (h->prefetching) return fail(SSC_ERR_STATE, "one FASTA record can be prefetched at a time");
+	int rc = check_fasta_geometry(n_bases, line_bases, line_width);
+	if (rc) return rc;
+	CK(cudaSetDevice(h->device));
+	if (!h->upload) CK(cudaStreamCreateWithFlags(&h->upload, cudaStreamNonBlocking));
+	if (!h->evRefFree) CK(cudaEventCreateWithFlags(&h->evRefFree, cudaEventDisableTiming));
+	// the second buffer set was the current reference until the last adoption: its readers are in the compute stream by now
+	CK(cudaEventRecord(h->evRefFree, h->compute));
+	h->prefetching = true;
+	h->prefetchRc = 0; h->prefetchErr.clear();
+	h->prefetchBases = n_bases; h->prefetchRaw = raw_len; h->prefetchOther = 0;
+	h->prefetchThread = std::thread([=]() {
+		h->prefetchRc = upload_fasta_record(h, 1, h->upload, h->d_ref2, h->d_raw2, h->d_other2, h->evRefFree, fd, file_offset, raw_len, n_bases,
+		                                    line_bases, line_width, &h->prefetchOther);
+		if (h->prefetchRc) h->prefetchErr = g_err;          // (this thread's message, for the adopting thread)
+	});
+	return SSC_OK;
+}
+
+int ssc_reference_adopt_prefetched(ssc_handle* h, uint64_t* n_other) {
+	if (!h) return fail(SSC_ERR_INVALID, "null handle");
+	if (!h->prefetching) return fail(SSC_ERR_STATE, "no FASTA record was prefetched");
+	h->prefetchThread.join();
+	h->prefetching = false;
+	if (h->prefetchRc) return fail(h->prefetchRc, "%s", h->prefetchErr.c_str());
+	std::swap(h->d_ref, h->d_ref2); std::swap(h->d_raw, h->d_raw2); std::swap(h->d_other, h->d_other2);
+	h->refSize = h->prefetchBases;
+	h->stats.h2d_bytes += h->prefetchRaw;
+	h->stats.launches += 1;
+	if (n_other) *n_other = h->prefetchOther;
 	return SSC_OK;
 }
 

@@ -11,7 +11,7 @@ from . import abi
 from .paths import LIB_CUDA
 
 SYMBOLS = ["ssc_last_error", "ssc_version", "ssc_create", "ssc_destroy", "ssc_set_option", "ssc_set_profile",
-           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_reference_upload_fasta", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
+           "ssc_genome_reserve", "ssc_genome_append", "ssc_genome_size", "ssc_reference_upload", "ssc_reference_upload_fasta", "ssc_reference_prefetch_fasta", "ssc_reference_adopt_prefetched", "ssc_genome_append_ref", "ssc_genome_poke", "ssc_genome_read", "ssc_gc_census", "ssc_set_plan", "ssc_generate",
            "ssc_generate_device", "ssc_get_stats", "ssc_reset_stats", "ssc_table_lookup_host", "ssc_sub_lookup_host", "ssc_gzip_member_host", "ssc_issue_floor"]
 
 _lib = None
@@ -36,6 +36,8 @@ def lib():
         L.ssc_reference_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
         L.ssc_reference_upload_fasta.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                                  C.POINTER(C.c_uint64)]
+        L.ssc_reference_prefetch_fasta.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ssc_reference_adopt_prefetched.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ssc_genome_append_ref.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
         L.ssc_genome_poke.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
         L.ssc_genome_read.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]

@@ -471,7 +471,19 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 	const int ploidy = cfg.num["ploidy"];
 	const bool useRefBuild = !getenv("SIMUSCOP_HOST_HAPLOTYPES");   // debugging: build every haplotype string on the host
 	int rc = 0;
-	for (auto& chr : chroms) {
+	// .fai geometry of a record as ssc_reference_upload_fasta wants it; false: not usable for the device path
+	struct Geom { uint64_t off, rawLen, n; uint32_t lb, lw; };
+	auto geom_of = [&](const std::string& c, Geom& g) -> bool {
+		const FastaEntry* e = fasta.entry(c);
+		if (!useRefBuild || !e || e->line_blen <= 0 || e->length <= 0) return false;
+		const uint64_t lines = (uint64_t)((e->length - 1) / e->line_blen);                 // full lines in front of the last one
+		g.off = (uint64_t)e->offset; g.n = (uint64_t)e->length; g.lb = (uint32_t)e->line_blen; g.lw = (uint32_t)e->line_len;
+		g.rawLen = g.n + lines * (uint64_t)(e->line_len - e->line_blen);
+		return true;
+	};
+	bool prefetched = false;                     // the record of the chromosome about to be processed is being read in the background
+	for (size_t ci = 0; ci < chroms.size(); ci++) {
+		const std::string& chr = chroms[ci];
 		std::vector<Segment>& v = segs[popu][chr];
 		ChrLayout& L = layout[chr];
 		L.base.assign(v.size(), std::vector<int64_t>(ploidy, -1));
@@ -483,22 +495,28 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		// insertion / deletion variants as a splice list of slice runs and inserted literals (Segment::generateSegSequences'
 		// insert / erase arithmetic runs on the list instead of on strings), SNP / SNV alleles poked in afterwards.  The host
 		// reads and upper-cases the chromosome only when it needs the string itself: IUPAC codes in the record (the count
-		// comes back from the unfold kernel), in an inserted sequence or in an allele.
+		// comes back from the unfold kernel), in an inserted sequence or in an allele.  While this chromosome is processed, the
+		// record of the next one is read and unfolded in the background (ssc_reference_prefetch_fasta).
 		const FastaEntry* fe = fasta.entry(chr);
 		const size_t chrLen = fe ? (size_t)fe->length : 0;
 		bool needHost = !useRefBuild || !fe || fe->line_blen <= 0;
 		bool devRef = false;
-		if (useRefBuild && fe && fe->line_blen > 0 && chrLen > 0) {
-			const uint64_t lines = (uint64_t)((chrLen - 1) / (size_t)fe->line_blen);          // full lines in front of the last one
-			const uint64_t rawLen = (uint64_t)chrLen + lines * (uint64_t)(fe->line_len - fe->line_blen);
+		Geom g;
+		if (geom_of(chr, g)) {
 			uint64_t nOther = 0;
 			for (ssc_handle* dev : devs) {
-				rc = ssc_reference_upload_fasta(dev, fasta.fd(), (uint64_t)fe->offset, rawLen, (uint64_t)chrLen, (uint32_t)fe->line_blen,
-				                                (uint32_t)fe->line_len, &nOther);
+				rc = prefetched ? ssc_reference_adopt_prefetched(dev, &nOther)
+				                : ssc_reference_upload_fasta(dev, fasta.fd(), g.off, g.rawLen, g.n, g.lb, g.lw, &nOther);
 				if (rc) return rc;
 			}
 			devRef = true;
 			if (nOther > 0) needHost = true;
+		}
+		prefetched = false;
+		Geom gn;
+		if (ci + 1 < chroms.size() && geom_of(chroms[ci + 1], gn)) {
+			for (ssc_handle* dev : devs) { rc = ssc_reference_prefetch_fasta(dev, fasta.fd(), gn.off, gn.rawLen, gn.n, gn.lb, gn.lw); if (rc) return rc; }
+			prefetched = true;
 		}
 		static const std::string noSeq;
 		const std::string& chrSeq = needHost ? fasta.chromosome(chr) : noSeq;
