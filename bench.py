@@ -334,7 +334,7 @@ def main():
         if rank == 0:
             nbt = max(1, st["timed_batches"])
             print(json.dumps({"opts": a.opts, "value": bases / dt, "ms_per_step": 1000.0 * dt / a.steps, "gen_ms": st["gen_kernel_ms"] / nbt,
-                              "pass2_ms": st["compact_kernel_ms"] / nbt, "profile": a.profile}))
+                              "pass2_ms": st["compact_kernel_ms"] / nbt, "profile": a.profile, "host_plan_and_upload_s": round(t_plan, 3)}))
         gen.close(); job.close()
         return 0
 

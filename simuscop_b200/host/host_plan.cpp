@@ -225,6 +225,17 @@ static int gc_percent(const char* s, size_t n) {
 	return 100 * gc / (int)(n - nn);
 }
 
+// fn(lo, hi, r) over R contiguous ranges of [0, n), each on its own thread; the ranges ascend with r, so results that are
+// concatenated in range order are in element order whatever R is
+static unsigned plan_threads() { return std::max(1u, std::min(16u, std::thread::hardware_concurrency())); }
+template <class F> static void parallel_ranges(size_t n, unsigned R, F fn) {
+	if (R <= 1 || n < 2) { fn((size_t)0, n, 0u); return; }
+	std::vector<std::thread> th;
+	for (unsigned r = 1; r < R; r++) th.emplace_back(fn, n * r / R, n * (r + 1) / R, r);
+	fn((size_t)0, n / R, 0u);
+	for (auto& t : th) t.join();
+}
+
 static inline bool is_acgtn(char ch) { const char c = (char)(ch & 0xDF); return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N'; }   // either case: haplotypes are upper-cased last (Segment.cpp:448-458)
 
 namespace {
@@ -609,19 +620,35 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		}
 		for (size_t k = 0; k < v.size(); k++) if (!hostGc[k]) { haps[k].clear(); haps[k].shrink_to_fit(); }
 		double t2 = PhaseTimers::now();
-		// census of every bin of the chromosome in one call
+		// census of every bin of the chromosome in one call.  The per-bin passes of this block (bin enumeration, census intervals,
+		// GC percentages, weights) run over contiguous segment ranges on a few host threads; everything they produce is
+		// position-determined, only the getGCFactor draws are ordered (see below).
+		const unsigned R = v.size() >= 8 ? std::min<unsigned>(plan_threads(), (unsigned)v.size()) : 1u;
 		std::vector<std::vector<BinSpec>> specs(v.size());
-		std::vector<int64_t> starts; std::vector<int32_t> lens;
-		for (size_t k = 0; k < v.size(); k++) {
-			if (v[k].weighted) continue;
-			enumerate_bins(v[k], L.hapLen[k], specs[k]);
-			if (hostGc[k]) continue;
-			for (auto& sp : specs[k]) {
-				if (sp.kind == 2) continue;
-				starts.push_back(L.base[k][sp.hap] + sp.gcStart);
-				lens.push_back((int32_t)sp.gcLen);
+		std::vector<size_t> cenOff(v.size() + 1, 0);          // census intervals of segment k: [cenOff[k], cenOff[k+1])
+		parallel_ranges(v.size(), R, [&](size_t lo, size_t hi, unsigned) {
+			for (size_t k = lo; k < hi; k++) {
+				if (v[k].weighted) continue;
+				enumerate_bins(v[k], L.hapLen[k], specs[k]);
+				size_t n = 0;
+				if (!hostGc[k]) for (auto& sp : specs[k]) n += sp.kind != 2;
+				cenOff[k + 1] = n;
 			}
-		}
+		});
+		for (size_t k = 0; k < v.size(); k++) cenOff[k + 1] += cenOff[k];
+		std::vector<int64_t> starts(cenOff[v.size()]); std::vector<int32_t> lens(cenOff[v.size()]);
+		parallel_ranges(v.size(), R, [&](size_t lo, size_t hi, unsigned) {
+			for (size_t k = lo; k < hi; k++) {
+				if (v[k].weighted || hostGc[k]) continue;
+				size_t o = cenOff[k];
+				for (auto& sp : specs[k]) {
+					if (sp.kind == 2) continue;
+					starts[o] = L.base[k][sp.hap] + sp.gcStart;
+					lens[o] = (int32_t)sp.gcLen;
+					o++;
+				}
+			}
+		});
 		std::vector<int32_t> cgc(starts.size()), cnn(starts.size());
 		g_tm.enumerate += PhaseTimers::now() - t2;
 		rc = ssc_gc_census(devs[0], starts.data(), lens.data(), (int64_t)starts.size(), cgc.data(), cnn.data());
@@ -631,35 +658,51 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 		// (Profile.cpp:1409-1415), so the draws of one percentage only depend on the order of the bins with that percentage:
 		// the 101 streams are independent and are advanced by several threads, each stream in bin order -- the values are
 		// the ones a single pass over the bins would draw.
-		size_t q = 0, flat = 0;
+		size_t flat = 0;
 		std::vector<std::vector<int>> gcs(v.size());
 		std::vector<size_t> flatOff(v.size(), 0);
-		for (size_t k = 0; k < v.size(); k++) {
-			if (v[k].weighted) continue;
-			std::vector<int>& gc = gcs[k];
-			gc.assign(specs[k].size(), 0);
-			flatOff[k] = flat; flat += specs[k].size();
-			for (size_t b = 0; b < specs[k].size(); b++) {
-				if (specs[k][b].kind == 2) continue;
-				if (hostGc[k]) { gc[b] = gc_percent(haps[k][specs[k][b].hap].data() + specs[k][b].gcStart, (size_t)specs[k][b].gcLen); continue; }
-				// calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303: empty -> 0, any N -> -1, else 100*gc/n (integer)
-				const int32_t n = lens[q];
-				gc[b] = n == 0 ? 0 : (cnn[q] > 0 ? -1 : 100 * cgc[q] / n);
-				q++;
+		for (size_t k = 0; k < v.size(); k++) { if (v[k].weighted) continue; flatOff[k] = flat; flat += specs[k].size(); }
+		// per range and percentage: how many draws (counting sort, so that byGc[g] lists its bins in bin order)
+		std::vector<std::vector<uint32_t>> cnt(R, std::vector<uint32_t>(101, 0));
+		parallel_ranges(v.size(), R, [&](size_t lo, size_t hi, unsigned r) {
+			for (size_t k = lo; k < hi; k++) {
+				if (v[k].weighted) continue;
+				std::vector<int>& gc = gcs[k];
+				gc.assign(specs[k].size(), 0);
+				size_t q = cenOff[k];
+				for (size_t b = 0; b < specs[k].size(); b++) {
+					if (specs[k][b].kind == 2) continue;
+					if (hostGc[k]) gc[b] = gc_percent(haps[k][specs[k][b].hap].data() + specs[k][b].gcStart, (size_t)specs[k][b].gcLen);
+					else {
+						// calculateGCPercent, lib/mydefine/MyDefine.cpp:279-303: empty -> 0, any N -> -1, else 100*gc/n (integer)
+						const int32_t n = lens[q];
+						gc[b] = n == 0 ? 0 : (cnn[q] > 0 ? -1 : 100 * cgc[q] / n);
+						q++;
+					}
+					if (gc[b] >= 0 && gc[b] <= 100) cnt[r][gc[b]]++;
+				}
 			}
-		}
+		});
 		std::vector<double> factors(flat, 0.0);
 		{
 			std::vector<std::vector<uint32_t>> byGc(101);
-			for (size_t k = 0; k < v.size(); k++) {
-				if (v[k].weighted) continue;
-				for (size_t b = 0; b < specs[k].size(); b++) {
-					const int g = gcs[k][b];
-					if (specs[k][b].kind != 2 && g >= 0 && g <= 100) byGc[g].push_back((uint32_t)(flatOff[k] + b));
-				}
+			std::vector<std::vector<size_t>> at(R, std::vector<size_t>(101, 0));
+			for (int g = 0; g <= 100; g++) {
+				size_t tot = 0;
+				for (unsigned r = 0; r < R; r++) { at[r][g] = tot; tot += cnt[r][g]; }
+				byGc[g].resize(tot);
 			}
-			const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-			std::vector<std::vector<double>> drawn(101);
+			parallel_ranges(v.size(), R, [&](size_t lo, size_t hi, unsigned r) {
+				std::vector<size_t> o = at[r];
+				for (size_t k = lo; k < hi; k++) {
+					if (v[k].weighted) continue;
+					for (size_t b = 0; b < specs[k].size(); b++) {
+						const int g = gcs[k][b];
+						if (specs[k][b].kind != 2 && g >= 0 && g <= 100) byGc[g][o[g]++] = (uint32_t)(flatOff[k] + b);
+					}
+				}
+			});
+			const unsigned T = plan_threads();
 			std::atomic<int> next(0);
 			auto run = [&]() {
 				for (int g = next.fetch_add(1); g <= 100; g = next.fetch_add(1)) {
@@ -668,13 +711,13 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 					// are 8 bytes apart in memory, neighbouring percentages would fight over the same cache line
 					std::default_random_engine eng = prof.gcEng[g];
 					std::normal_distribution<double> dist = prof.gcDist[g];
-					std::vector<double>& out = drawn[g];
-					out.resize(byGc[g].size());
+					std::vector<double> out(byGc[g].size());               // drawn into private memory, scattered in one go
 					for (size_t k = 0; k < out.size(); k++) {
-						double v = dist(eng);
-						while (v < 0) v = dist(eng);                     // Profile::getGCFactor, Profile.cpp:1507-1517
-						out[k] = v;
+						double x = dist(eng);
+						while (x < 0) x = dist(eng);                     // Profile::getGCFactor, Profile.cpp:1507-1517
+						out[k] = x;
 					}
+					for (size_t k = 0; k < out.size(); k++) factors[byGc[g][k]] = out[k];
 					prof.gcEng[g] = eng; prof.gcDist[g] = dist;
 				}
 			};
@@ -685,13 +728,13 @@ int Job::device_weights(const std::string& popu, const std::vector<ssc_handle*>&
 				run();
 				for (auto& t : th) t.join();
 			}
-			for (int g = 0; g <= 100; g++)
-				for (size_t k = 0; k < drawn[g].size(); k++) factors[byGc[g][k]] = drawn[g][k];
 		}
-		for (size_t k = 0; k < v.size(); k++) {
-			if (v[k].weighted) continue;
-			weights_from_gc(v[k], specs[k], gcs[k].data(), factors.data() + flatOff[k]);
-		}
+		parallel_ranges(v.size(), R, [&](size_t lo, size_t hi, unsigned) {
+			for (size_t k = lo; k < hi; k++) {
+				if (v[k].weighted) continue;
+				weights_from_gc(v[k], specs[k], gcs[k].data(), factors.data() + flatOff[k]);
+			}
+		});
 		g_tm.build += t1 - t0; g_tm.upload += t2 - t1; g_tm.census += t3 - t2; g_tm.gc += PhaseTimers::now() - t3;
 	}
 	return 0;
@@ -879,28 +922,43 @@ int Job::prepare_sample_multi(int s, const std::vector<ssc_handle*>& devs, const
 				}
 			}
 			const ChrLayout& L = onDevice ? layout[chr] : hostLayout;
+			// flat ssc_bin records of the chromosome: offsets first, then the segments filled side by side on host threads
+			std::vector<size_t> binOff(v.size() + 1, bins.size());
+			std::vector<uint32_t> segsizes(v.size(), 0);
+			const int32_t segId0 = (int32_t)segments.size();
 			for (size_t k = 0; k < v.size(); k++) {
 				Segment& sg = v[k];
 				uint64_t seqSize = 0;
 				for (int h = 0; h < ploidy; h++) seqSize += L.hapLen[k][h];
-				const uint32_t segsize = (uint32_t)((unsigned int)seqSize / (unsigned int)sg.CN);   // Segment.cpp:712-714
+				segsizes[k] = (uint32_t)((unsigned int)seqSize / (unsigned int)sg.CN);   // Segment.cpp:712-714
+				binOff[k + 1] = binOff[k] + sg.bins.size();
 				ssc_segment ss;
-				ss.first_bin = (int64_t)bins.size(); ss.n_bins = (int64_t)sg.bins.size();
+				ss.first_bin = (int64_t)binOff[k]; ss.n_bins = (int64_t)sg.bins.size();
 				ss.name_offset = nameOff; ss.name_len = (int32_t)nm.size();
-				const int32_t segId = (int32_t)segments.size();
-				for (auto& b : sg.bins) {
-					ssc_bin sb;
-					memset(&sb, 0, sizeof(sb));
-					const bool present = b.hap >= 0 && b.hap < ploidy && L.base[k][b.hap] >= 0;
-					sb.hap_base = present ? L.base[k][b.hap] : 0;
-					sb.contig_end = present ? L.contigEnd[b.hap] : 0;
-					sb.spos = (int32_t)b.spos; sb.epos = (int32_t)b.epos;
-					sb.segsize = segsize;
-					sb.read_count = (present && sg.readCount != 0) ? b.rc : 0;   // Segment::yieldReads early return, Segment.cpp:675-677
-					sb.segment = segId;
-					bins.push_back(sb);
-				}
 				segments.push_back(ss);
+			}
+			bins.resize(binOff[v.size()]);
+			parallel_ranges(v.size(), v.size() >= 8 ? std::min<unsigned>(plan_threads(), (unsigned)v.size()) : 1u, [&](size_t lo, size_t hi, unsigned) {
+				for (size_t k = lo; k < hi; k++) {
+					const Segment& sg = v[k];
+					ssc_bin* out = bins.data() + binOff[k];
+					for (const Bin& b : sg.bins) {
+						ssc_bin sb;
+						memset(&sb, 0, sizeof(sb));
+						const bool present = b.hap >= 0 && b.hap < ploidy && L.base[k][b.hap] >= 0;
+						sb.hap_base = present ? L.base[k][b.hap] : 0;
+						sb.contig_end = present ? L.contigEnd[b.hap] : 0;
+						sb.spos = (int32_t)b.spos; sb.epos = (int32_t)b.epos;
+						sb.segsize = segsizes[k];
+						sb.read_count = (present && sg.readCount != 0) ? b.rc : 0;   // Segment::yieldReads early return, Segment.cpp:675-677
+						sb.segment = segId0 + (int32_t)k;
+						*out++ = sb;
+					}
+				}
+			});
+			for (size_t k = 0; k < v.size(); k++) {
+				Segment& sg = v[k];
+				const uint32_t segsize = segsizes[k];
 				if (pw.fp && !flatDump) {
 					std::string r;
 					PlanWriter::app<int32_t>(r, sg.idx); PlanWriter::app<int32_t>(r, sg.CN);
