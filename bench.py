@@ -508,6 +508,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "achieved_step": alg_bytes / nb / (T_dev / steps_done) / 1e9 if T_dev > 0 else None,
+                         "frac_step": alg_bytes / nb / (T_dev / steps_done) / 1e9 / peak if T_dev > 0 else None,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "generate_slots_kernel",
                          "kernel_ms_per_launch": gen_ms, "pass2_ms_per_launch": st["compact_kernel_ms"] / nb,
                          "algorithmic_bytes_per_launch": alg_bytes / nb,
@@ -521,8 +523,10 @@ def main():
                                            "stores of an indel-free read"},
                          "ncu": ncu,
                          "note": "issue-bound kernel, not HBM-bound (DESIGN.md section 4).  kernel_ms_per_launch is the CUDA-event time "
-                                 "of generate_slots_kernel (pass 1), pass2_ms_per_launch that of the scan of the blob lengths and the "
-                                 "move of the blobs into the dense ordered slab"},
+                                 "of generate_slots_kernel (pass 1; on the SMs the concurrent mover leaves it: 140 of 148), "
+                                 "pass2_ms_per_launch that of the scan of the blob lengths (+ the stand-alone move of the call's last "
+                                 "batch, spread over the batches); the moves of the other batches run under the next generation "
+                                 "launch on 8 SMs.  achieved_step / frac_step: the same bytes over the device time of a whole step"},
         }
         if world == 1 and not a.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)          # the reference gets every host core again
