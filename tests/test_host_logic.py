@@ -409,3 +409,29 @@ def test_splice_lists_equal_haplotype_strings(kind, seed, built, workdir):
         pytest.skip("input rejected by the front end (as by the reference): %s" % r.stderr.strip().split("\n")[-1][:120])
     bad, n, k = [int(x) for x in [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()[1:]]
     assert bad == 0 and n > 0, (bad, n, k)
+
+
+def test_bench_count_bases_streams_exactly(tmp_path):
+    """bench.py's reference arm counts the emitted bases of multi-GB FASTQ files in constant memory: the streaming count must
+    equal the naive one, also when a buffer boundary cuts a line."""
+    import gzip
+    import bench
+    data = gzip.open(os.path.join(GOLD, "pe_tiny_1.fq.gz")).read()
+    p = tmp_path / "a.fq"
+    p.write_bytes(data * 3)
+    want = 3 * sum(len(x) for x in data.split(b"\n")[1::4])
+    assert bench.count_bases([str(p)]) == want
+    real_open = open
+
+    class Tiny:                                # 1000-byte reads: every kind of boundary position occurs
+        def __init__(self, f): self.f = f
+        def read(self, n): return self.f.read(min(n, 1000))
+        def __enter__(self): return self
+        def __exit__(self, *a): self.f.close()
+    import builtins
+    old = builtins.open
+    builtins.open = lambda path, mode="r", *a, **k: Tiny(real_open(path, mode, *a, **k)) if str(path) == str(p) else real_open(path, mode, *a, **k)
+    try:
+        assert bench.count_bases([str(p)]) == want
+    finally:
+        builtins.open = old
