@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--ref-slice-mb", type=int, default=0, help="--impl reference: size of the one-chromosome slice (default max(320, 16 x threads))")
     ap.add_argument("--file-dirs", default="/dev/shm,workdir", help="directories the e2e_file legs write to (workdir = --workdir)")
-    ap.add_argument("--writer-threads", type=int, default=8)
+    ap.add_argument("--writer-threads", type=int, default=2, help="threads of the file writer (its default mode uses one stream per file)")
     ap.add_argument("--opts", default="", help="experiments: comma-separated ssc_set_option settings, e.g. carry_pass2=0,prefetch_windows=0")
     ap.add_argument("--device-only", action="store_true", help="experiments: only the device-resident leg")
     ap.add_argument("--cli-wall", action="store_true", help="also time the drop-in CLI on the whole job (plain FASTQ to /dev/shm when it fits, gzip to --workdir)")
@@ -495,9 +495,10 @@ def main():
                             "uploaded once from host memory during setup (setup_s); the sink only counts bytes -- e2e_file is the "
                             "same call with the files written"},
             "e2e_file": None if e2e_file is None else dict(
-                e2e_file, note="the same call with the drop-in CLI's file writer as the sink: both FASTQ files written (pwrite by %d "
-                               "threads at final offsets, no fsync: the reference's SeqWriter does not sync either), files closed inside "
-                               "the timed region" % a.writer_threads),
+                e2e_file, note="the same call with the drop-in CLI's file writer as the sink: both FASTQ files written (one pwrite "
+                               "stream per file, the two files side by side: buffered writes to one file serialise on its inode "
+                               "lock, tools/fs_probe.c; no fsync: the reference's SeqWriter does not sync either), files closed "
+                               "inside the timed region"),
             "e2e_file_all": file_out,
             "e2e_gzip": None if gz is None else {
                 "value": gz_bases / T_gz, "unit": "bases/s", "d2h_bytes_per_step": int(gz_d2h / steps_done),

@@ -24,20 +24,32 @@ struct ssh_job {
 
 // ------------------------------------------------------------------------------------------------
 // Output side: SeqWriter's role (lib/seqwriter/SeqWriter.cpp:41-54: append the slab(s) to the FASTQ file(s), both files
-// advancing together) at the rate a GPU produces slabs.  A slab of ~0.7 GB per file is cut into chunks that a small pool of
-// threads pwrite()s at their final offsets in parallel (page-cache / tmpfs copies scale with threads; a real device sees a
-// deeper queue); the call returns when the slab is on its way to the file, because the pinned slab is reused afterwards.
+// advancing together) at the rate a GPU produces slabs.  The call returns when the slab is in the file (page cache), because
+// the pinned slab is reused afterwards.
+//
+// What bounds it (tools/fs_probe.c on the pool's boxes, profiles/r02w_fs_probe.jsonl): buffered writes to ONE file serialise
+// on its inode lock -- 3.6-5.4 GB/s into one file with 1, 4 or 16 threads, against 15-38 GB/s into 4-16 separate files --
+// and stores through a shared mapping of the file do not take that lock but pay a page fault per 4 KB (tmpfs 6-7 GB/s per
+// file with 4-16 threads, ext4 3-4).  So a slab of ~0.7 GB per file is cut into 8 MB chunks and written from both ends:
+//   * one STREAM thread per file pwrite()s the file's chunks front to back (threads 0 and 1 of the pool);
+//   * in the modes with mappings the other threads, and a stream thread whose file is finished, copy chunks into a
+//     MAP_SHARED mapping of the slab's file range, back to front, in whichever file has more left.
+// SIMUSCOP_WRITER_MODE = pwrite (streams only) | mmap (mappings only) | hybrid (both; needs more than two threads).
 // ------------------------------------------------------------------------------------------------
 struct ssh_writer {
+	enum Mode { PWRITE = 0, MMAP = 1, HYBRID = 2 };
+	static const size_t CH = 8u << 20;
 	int fd[2] = {-1, -1};
 	uint64_t off[2] = {0, 0};
 	int nThreads = 1;
+	int mode = PWRITE;
 	std::vector<std::thread> pool;
 	std::mutex mu;
 	std::condition_variable cvWork, cvDone;
-	struct Chunk { int fd; const char* p; size_t n; uint64_t off; char* dst; };   // dst != nullptr: copy into the mapped file
-	std::vector<Chunk> queue;
-	size_t next = 0, inFlight = 0;
+	// the slab of one file in flight: chunks [front, back) are still to be taken
+	struct FileJob { int fd = -1; const char* p = nullptr; size_t len = 0; uint64_t off = 0; char* base = nullptr; size_t front = 0, back = 0; };
+	FileJob job[2];
+	size_t inFlight = 0;
 	bool stop = false, noMap = false;
 	int err = 0;
 	// turnstile for several producers (one per GPU) that deliver batches out of order: batch k is written when every
@@ -53,67 +65,84 @@ struct ssh_writer {
 		}
 		return 0;
 	}
-	static int put(const Chunk& c) {
-		if (!c.dst) return pwrite_all(c.fd, c.p, c.n, c.off);
+	static int put(const FileJob& j, size_t chunk, bool mapped) {
+		const size_t o = chunk * CH, n = std::min(CH, j.len - o);
+		if (!mapped) return pwrite_all(j.fd, j.p + o, n, j.off + o);
+		char* dst = j.base + o;
 #ifdef MADV_POPULATE_WRITE
 		// fault the chunk's pages in one call (page-aligned interior) instead of one trap per page
 		{
-			const uintptr_t a = ((uintptr_t)c.dst + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)c.dst + c.n) & ~(uintptr_t)4095;
+			const uintptr_t a = ((uintptr_t)dst + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)dst + n) & ~(uintptr_t)4095;
 			if (b > a) madvise((void*)a, b - a, MADV_POPULATE_WRITE);
 		}
 #endif
-		memcpy(c.dst, c.p, c.n);
+		memcpy(dst, j.p + o, n);
 		return 0;
 	}
-	void worker() {
+	bool left() const { return job[0].front < job[0].back || job[1].front < job[1].back; }
+	// the next chunk for pool thread `id` (called with mu held): false when there is nothing this thread may take
+	bool take(int id, int* file, size_t* chunk, bool* mapped) {
+		const bool streams = mode != MMAP;
+		if (streams && id < 2 && job[id].front < job[id].back) { *file = id; *chunk = job[id].front++; *mapped = false; return true; }
+		// a mapper, or a stream thread without work of its own: the file with more left, from the back
+		int f = (job[0].back - job[0].front) >= (job[1].back - job[1].front) ? 0 : 1;
+		for (int k = 0; k < 2; k++, f ^= 1) {
+			FileJob& j = job[f];
+			if (j.front >= j.back) continue;
+			if (j.base) { *file = f; *chunk = --j.back; *mapped = true; return true; }
+			// not mapped: left to the file's own stream -- or, where there are no streams (mmap mode that could not map), to anybody
+			if (!streams) { *file = f; *chunk = j.front++; *mapped = false; return true; }
+		}
+		return false;
+	}
+	void worker(int id) {
 		std::unique_lock<std::mutex> lk(mu);
 		while (true) {
-			cvWork.wait(lk, [&] { return stop || next < queue.size(); });
-			if (stop && next >= queue.size()) return;
-			const Chunk c = queue[next++];
+			int f = 0; size_t c = 0; bool mapped = false, got = false;
+			cvWork.wait(lk, [&] { return stop || (got = take(id, &f, &c, &mapped)); });
+			if (!got) return;                                  // stop
 			inFlight++;
+			const FileJob j = job[f];
 			lk.unlock();
-			const int e = put(c);
+			const int e = put(j, c, mapped);
 			lk.lock();
 			if (e && !err) err = e;
 			inFlight--;
-			if (next >= queue.size() && inFlight == 0) cvDone.notify_all();
+			if (!left() && inFlight == 0) cvDone.notify_all();
 		}
 	}
-	// Both slabs to their files at the running offsets; returns when written.  With worker threads the file is extended and
-	// the slab's range mapped (MAP_SHARED): the workers copy their chunks into the mapping, which scales with the threads --
-	// buffered pwrite()s to ONE file serialise on its inode lock, so a pool of them writes no faster than two threads.
-	// Where the mapping fails (not a regular file) the chunks are pwrite()n.
+	// Both slabs to their files at the running offsets; returns when written.
 	int write_slabs(const char* b1, size_t l1, const char* b2, size_t l2) {
-		static const size_t CH = 8u << 20;
 		std::unique_lock<std::mutex> lk(mu);
-		queue.clear(); next = 0;
 		const char* bufs[2] = {b1, b2}; const size_t lens[2] = {l1, fd[1] >= 0 ? l2 : 0};
 		void* maps[2] = {nullptr, nullptr}; size_t mapLen[2] = {0, 0};
 		for (int f = 0; f < 2; f++) {
+			job[f] = FileJob();
 			if (!lens[f]) continue;
-			char* base = nullptr;
-			if (!pool.empty() && !noMap) {
+			job[f].fd = fd[f]; job[f].p = bufs[f]; job[f].len = lens[f]; job[f].off = off[f];
+			job[f].back = (lens[f] + CH - 1) / CH;
+			const bool wantMap = !pool.empty() && !noMap && (mode == MMAP || (mode == HYBRID && nThreads > 2));
+			if (wantMap) {
 				const uint64_t a = off[f] & ~(uint64_t)4095;
 				if (ftruncate(fd[f], (off_t)(off[f] + lens[f])) == 0) {
 					void* m = mmap(nullptr, (size_t)(off[f] + lens[f] - a), PROT_READ | PROT_WRITE, MAP_SHARED, fd[f], (off_t)a);
-					if (m != MAP_FAILED) { maps[f] = m; mapLen[f] = (size_t)(off[f] + lens[f] - a); base = (char*)m + (off[f] - a); }
+					if (m != MAP_FAILED) { maps[f] = m; mapLen[f] = (size_t)(off[f] + lens[f] - a); job[f].base = (char*)m + (off[f] - a); }
 					else noMap = true;
 				} else noMap = true;
 			}
-			for (size_t o = 0; o < lens[f]; o += CH)
-				queue.push_back(Chunk{fd[f], bufs[f] + o, std::min(CH, lens[f] - o), off[f] + o, base ? base + o : nullptr});
 			off[f] += lens[f];
 		}
-		if (queue.empty()) return 0;
+		if (!left()) return err;
 		if (pool.empty()) {           // single-threaded: write here
-			for (const Chunk& c : queue) { const int e = put(c); if (e && !err) err = e; }
-			queue.clear();
+			for (int f = 0; f < 2; f++) {
+				for (size_t c = job[f].front; c < job[f].back; c++) { const int e = put(job[f], c, false); if (e && !err) err = e; }
+				job[f] = FileJob();
+			}
 			return err;
 		}
 		cvWork.notify_all();
-		cvDone.wait(lk, [&] { return next >= queue.size() && inFlight == 0; });
-		for (int f = 0; f < 2; f++) if (maps[f]) munmap(maps[f], mapLen[f]);
+		cvDone.wait(lk, [&] { return !left() && inFlight == 0; });
+		for (int f = 0; f < 2; f++) { if (maps[f]) munmap(maps[f], mapLen[f]); job[f] = FileJob(); }
 		return err;
 	}
 };
@@ -225,7 +254,10 @@ int ssh_writer_open(const char* path1, const char* path2, int threads, ssh_write
 		return SSC_ERR_SINK;
 	}
 	w->nThreads = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
-	if (w->nThreads > 1) for (int i = 0; i < w->nThreads; i++) w->pool.emplace_back([w] { w->worker(); });
+	if (const char* m = getenv("SIMUSCOP_WRITER_MODE"))
+		w->mode = strcmp(m, "mmap") == 0 ? ssh_writer::MMAP : (strcmp(m, "hybrid") == 0 ? ssh_writer::HYBRID : ssh_writer::PWRITE);
+	if (w->mode == ssh_writer::PWRITE && w->nThreads > 2) w->nThreads = 2;   // one stream per file: more threads would only queue on the inode locks
+	if (w->nThreads > 1) for (int i = 0; i < w->nThreads; i++) w->pool.emplace_back([w, i] { w->worker(i); });
 	*out = w;
 	return SSC_OK;
 }

@@ -359,8 +359,14 @@ def test_file_writer_sink_writes_ordered_slabs(built, tmp_path):
     hl.ssh_writer_close.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     sink = C.cast(hl.ssh_writer_sink(), abi.SINK_FN)
     rng = np.random.default_rng(3)
-    for threads, paired in ((1, True), (5, True), (3, False)):
-        p1, p2 = str(tmp_path / ("w%d_1.fq" % threads)), str(tmp_path / ("w%d_2.fq" % threads))
+    for threads, paired, mode in ((1, True, None), (5, True, None), (3, False, None), (5, True, "mmap"), (3, False, "mmap"),
+                                  (5, True, "hybrid"), (2, True, "hybrid"), (4, False, "hybrid")):
+        # default: one pwrite stream per file; SIMUSCOP_WRITER_MODE=mmap: the pool copies 8 MiB chunks into mappings of the
+        # files; hybrid: a stream per file from the front, the other threads through mappings from the back
+        os.environ.pop("SIMUSCOP_WRITER_MODE", None)
+        if mode:
+            os.environ["SIMUSCOP_WRITER_MODE"] = mode
+        p1, p2 = str(tmp_path / ("w%d%s_1.fq" % (threads, mode))), str(tmp_path / ("w%d%s_2.fq" % (threads, mode)))
         w = C.c_void_p()
         assert hl.ssh_writer_open(p1.encode(), p2.encode() if paired else None, threads, C.byref(w)) == 0
         want1, want2 = b"", b""
@@ -377,6 +383,7 @@ def test_file_writer_sink_writes_ordered_slabs(built, tmp_path):
             assert open(p2, "rb").read() == want2
         else:
             assert not os.path.exists(p2)
+    os.environ.pop("SIMUSCOP_WRITER_MODE", None)
     assert hl.ssh_writer_open(str(tmp_path / "no" / "such" / "dir.fq").encode(), None, 2, C.byref(C.c_void_p())) != 0
 
 

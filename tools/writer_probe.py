@@ -19,8 +19,10 @@ hl.ssh_writer_close.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c
 sink = C.cast(hl.ssh_writer_sink(), abi.SINK_FN)
 buf = np.random.default_rng(1).integers(0, 256, 256 << 20, dtype=np.uint8).tobytes()
 for d in sys.argv[1:] or ["/dev/shm", "/tmp"]:
-    for rep in range(2):
-        for th in (1, 2, 4, 8, 16):
+    for rep, mode, ths in ((0, "pwrite", (1, 2)), (1, "pwrite", (1, 2)), (0, "mmap", (4, 8, 16)), (0, "hybrid", (3, 4, 6, 8, 12, 16)),
+                           (1, "hybrid", (3, 4, 6, 8, 12, 16))):
+        os.environ["SIMUSCOP_WRITER_MODE"] = mode          # pwrite: one stream per file; mmap: chunk pool into mappings; hybrid: both
+        for th in ths:
             w = C.c_void_p()
             p1, p2 = os.path.join(d, "wprobe_1"), os.path.join(d, "wprobe_2")
             assert hl.ssh_writer_open(p1.encode(), p2.encode(), th, C.byref(w)) == 0
@@ -29,5 +31,5 @@ for d in sys.argv[1:] or ["/dev/shm", "/tmp"]:
                 assert sink(w, buf, len(buf), buf, len(buf), 0, 0) == 0
             hl.ssh_writer_close(w, None, None)
             dt = time.perf_counter() - t
-            print(json.dumps({"dir": d, "pass": rep, "threads": th, "GBps": round(8 * len(buf) / dt / 1e9, 2)}), flush=True)
+            print(json.dumps({"dir": d, "mode": mode, "pass": rep, "threads": th, "GBps": round(8 * len(buf) / dt / 1e9, 2)}), flush=True)
             os.remove(p1); os.remove(p2)
