@@ -41,8 +41,10 @@ int ssh_prepare_sample(ssh_job* job, int s, ssc_handle* dev, const char* dump_pa
 int ssh_selftest_splices(ssh_job* job, int64_t* haplotypes_checked, int64_t* segments_with_indels);
 
 /* Output side (the role of SeqWriter, lib/seqwriter/SeqWriter.cpp:41-54): an ordered FASTQ file writer whose sink can be
- * handed to ssc_generate with user = the writer.  path2 NULL = single-end.  Every slab is cut into chunks that `threads`
- * workers pwrite() at their final offsets (threads <= 1: written by the caller's thread). */
+ * handed to ssc_generate with user = the writer.  path2 NULL = single-end.  threads <= 1: slabs are written by the caller's
+ * thread; otherwise one pwrite() stream per file, the two files side by side (a file is a serial resource under its inode
+ * lock, so the default mode never uses more than two threads).  Environment SIMUSCOP_WRITER_MODE = mmap | hybrid: `threads`
+ * workers copy 8 MB chunks into shared mappings of the slab's file ranges (hybrid: beside the two streams). */
 typedef struct ssh_writer ssh_writer;
 int ssh_writer_open(const char* path1, const char* path2, int threads, ssh_writer** out);
 ssc_sink_fn ssh_writer_sink(void);
