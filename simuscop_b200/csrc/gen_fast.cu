@@ -225,19 +225,19 @@ __device__ __forceinline__ void lookup16(const WarpCtx& w, uint32_t rowIdx, uint
 	const uint32_t uh2 = u2 >> 16, uh3 = u3 >> 16;
 	const uint32_t k0 = lo & 0xffffu, k1 = lo >> 16, k2 = hi & 0xffffu;
 	uint32_t rc = hi >> 16;                                         // (ref, base) row: ref * 4 + base
-	rc += (uh2 > k0) + (uh2 > k1) + (uh2 > k2);
+	add_gt(rc, uh2, k0, 1u); add_gt(rc, uh2, k1, 1u); add_gt(rc, uh2, k2, 1u);
 	bool tie = (uh2 == k0) | (uh2 == k1) | (uh2 == k2);
 	if (passThrough) { rc = cur * 5u; tie = false; }
 	const uint32_t qa = w.qualBaseS + (rc * (uint32_t)w.B + binIdx) * (uint32_t)F_Q16_ROW;
-	uint32_t k = 0;                                                 // byte offset of the first key >= uh3: lower bound over 40 keys
-	add_lt(k, lds_u16(qa + k + 38), uh3, 40u);                      // steps of 20, 10, 5, 2, 1, 1 keys
-	add_lt(k, lds_u16(qa + k + 18), uh3, 20u);
-	add_lt(k, lds_u16(qa + k + 8), uh3, 10u);
-	add_lt(k, lds_u16(qa + k + 2), uh3, 4u);
-	add_lt(k, lds_u16(qa + k), uh3, 2u);
-	add_lt(k, lds_u16(qa + k), uh3, 2u);
-	tie |= lds_u16(qa + k) == uh3;                                  // (k <= 78: the last key of a row is read at most)
-	q = lds_u8(qa + 2u * F_Q16_KEYS + (k >> 1));
+	uint32_t kp = qa;                                               // address of the first key >= uh3: lower bound over 40 keys,
+	add_lt(kp, lds_u16(kp + 38), uh3, 40u);                         // steps of 20, 10, 5, 2, 1, 1 keys (a running address: one
+	add_lt(kp, lds_u16(kp + 18), uh3, 20u);                         // add less per step than row address + offset)
+	add_lt(kp, lds_u16(kp + 8), uh3, 10u);
+	add_lt(kp, lds_u16(kp + 2), uh3, 4u);
+	add_lt(kp, lds_u16(kp), uh3, 2u);
+	add_lt(kp, lds_u16(kp), uh3, 2u);
+	tie |= lds_u16(kp) == uh3;                                      // (offset <= 78: the last key of a row is read at most)
+	q = lds_u8(((qa + kp) >> 1) + 2u * F_Q16_KEYS);                 // symbol (kp - qa) / 2 of the row; qa + kp is even
 	uint32_t call = rc & 3u;
 	if (tie) {
 		// exact repeat on the 32-bit tables (global memory, L2)
